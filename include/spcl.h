@@ -1,0 +1,119 @@
+/*
+ * spcl.h -- C ABI of the B200-native self-paced supervised-contrastive loss.
+ *
+ * Drop-in boundary for ONE hot path of jizongFox/Self-paced-Contrastive-Learning:
+ * contrastyou/losses/contrast_loss3.py (SupConLoss1 :34-110, SelfPacedSupConLoss :113-222,
+ * exp_sim_temperature :25-31) plus the projector's L2-normalise tail
+ * (contrastyou/projectors/nn.py:29-36).  The reference is pure Python/PyTorch and has no FFI;
+ * these entry points are what a binding for that path would call (see INTEGRATION.md for the
+ * ctypes stub and the torch custom op built on it).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the library never allocates,
+ *     never synchronises the device and never throws: it validates, enqueues work on `stream`
+ *     and returns SPCL_OK or a negative error code (spcl_error_string() explains it).
+ *   - anchors: Z = [view-1 rows ; view-2 rows], N = n_total rows; S = Z Z^T / tau.
+ *   - labels: int32[N]; anchors i != j are positives iff labels[i] == labels[j]
+ *     (reference: torch.eq on the target, contrast_loss3.py:136, tiled 2x2, diagonal removed :163-167).
+ *   - tri-state mask (fp32 path only): uint8[n_half*n_half], 1 = positive, 0 = negative,
+ *     anything else = ignored (reference: mask == 1 / mask == 0, :130-131).
+ *   - mode: SPCL_MODE_NONE = SupConLoss1 (W == 1), HARD / SOFT = SelfPacedSupConLoss._self_paced_mask :207-214.
+ *   - row sharding: a call owns anchor rows [row_begin, row_end) against all N columns.
+ *   - row_stats: float[N][4] = { logD_i, 1/c_i, A_i, u_i } with logD_i the natural-log row
+ *     logsumexp over valid columns, c_i the positive count, A_i = sum_j W_ij P_ij / c_i and
+ *     u_i = A_i * exp(1/tau - logD_i).
+ *   - partials: float[3] = { sum_i (1/c_i) sum_j W P LLH , sum W P , sum P } accumulated with
+ *     atomicAdd (zero them first; all-reduce them across ranks when rows are sharded).
+ *   - scalars: float[4] = { loss, downgrade_ratio, grad scale, scale / N }.
+ */
+#ifndef SPCL_H_
+#define SPCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPCL_OK 0
+#define SPCL_ERR_INVALID_ARG (-1)
+#define SPCL_ERR_UNSUPPORTED (-2)
+#define SPCL_ERR_CUDA (-3)
+#define SPCL_ERR_NO_DRIVER (-4)
+
+#define SPCL_MODE_NONE 0
+#define SPCL_MODE_HARD 1
+#define SPCL_MODE_SOFT 2
+
+#define SPCL_DTYPE_F32 0
+#define SPCL_DTYPE_BF16 1
+#define SPCL_DTYPE_F16 2
+
+#define SPCL_TILE 128     /* anchor-block size of the tensor-core path */
+#define SPCL_MAX_D 256    /* embedding width limit of this build */
+
+typedef void* spcl_stream_t; /* cudaStream_t */
+
+int spcl_version(void);
+const char* spcl_error_string(int code);
+/* last CUDA error text seen by this thread inside the library (host string, never NULL) */
+const char* spcl_last_cuda_error(void);
+
+/* ---- projector tail: F.normalize(x, p=2, dim) (contrastyou/projectors/nn.py:35-36) -------------
+ * x is viewed as [outer, d, inner] and normalised along d: inner == 1 is ProjectionHead's [B, C]
+ * (heads.py:17), inner == H*W is DenseProjectionHead's NCHW (heads.py:113-114).
+ * y = x / max(||x||, eps); inv_norm[outer*inner] = 1 / max(||x||, eps) is kept for the backward. */
+int spcl_l2norm_fwd(const void* x, void* y, float* inv_norm, int dtype, int64_t outer, int64_t d, int64_t inner,
+                    float eps, spcl_stream_t stream);
+/* gx = inv_norm * (gy - y * sum_d(y * gy))  (exact when ||x|| >= eps) */
+int spcl_l2norm_bwd(const void* gy, const void* y, const float* inv_norm, void* gx, int dtype, int64_t outer,
+                    int64_t d, int64_t inner, spcl_stream_t stream);
+
+/* ---- operand packing for the tensor-core path ------------------------------------------------
+ * dst: bf16 [2n rows][d_pad] row-major; rows [0,n) <- z1, rows [n,2n) <- z2, columns d..d_pad zeroed.
+ * (replaces torch.cat at contrast_loss3.py:26) */
+int spcl_pack_views_bf16(const float* z1, const float* z2, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
+                         void* dst, int64_t d_pad, spcl_stream_t stream);
+
+/* per-128-anchor label signatures used to skip tiles without positives: int32[n_pad/128][4] */
+int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
+                         spcl_stream_t stream);
+
+/* ---- fused forward, tensor-core (tcgen05/TMEM/TMA) path --------------------------------------
+ * zb: bf16 [n_pad][d_pad] (n_pad % 128 == 0, rows >= n_total zero), labels: int32 [n_pad].
+ * acc: float [n_pad][4] scratch, zeroed by the call.  Writes row_stats for the owned rows and adds
+ * this call's partial sums into partials[3].  Replaces contrast_loss3.py:25-31,:157-197. */
+int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad, const int32_t* labels,
+                         const int32_t* sig, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
+                         int mode, float* acc, float* row_stats, float* partials, spcl_stream_t stream);
+
+/* ---- fused backward, tensor-core path --------------------------------------------------------
+ * row_stats must hold ALL N rows (all-gathered when sharded).  dz: float [row_end-row_begin][lddz],
+ * zeroed by the call; dz_i = grad_out * scale / (N tau) * sum_j T_ij z_j.  Replaces autograd of
+ * contrast_loss3.py:27,:180-197. */
+int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad, int32_t d,
+                         const int32_t* labels, const int32_t* sig, const float* row_stats, const float* scalars,
+                         const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
+                         int mode, float* dz, int64_t lddz, spcl_stream_t stream);
+
+/* ---- fp32 SIMT path: same contract with fp32 operands, exact-parity mode ----------------------
+ * z: float [n_total][ldz].  Exactly one of labels / tri may be non-NULL (tri needs n_half = N/2). */
+int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                        const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end, float inv_tau,
+                        float gamma, int mode, float* row_stats, float* partials, spcl_stream_t stream);
+int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                        const uint8_t* tri, int64_t n_half, const float* row_stats, const float* scalars,
+                        const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
+                        int mode, float* dz, int64_t lddz, spcl_stream_t stream);
+
+/* ---- scalar epilogue (after the optional all-reduce of partials) ------------------------------
+ * scalars = { loss, ratio, scale, scale / N }; scale = 1/ratio if correct_grad and ratio > 0
+ * (contrast_loss3.py:189-201).  A NaN loss is reported by the host wrapper as RuntimeError (:203). */
+int spcl_supcon_finalize(const float* partials, int64_t n_total, int correct_grad, float* scalars,
+                         spcl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCL_H_ */

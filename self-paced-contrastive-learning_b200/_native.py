@@ -1,0 +1,98 @@
+"""ctypes binding of the C ABI declared in ``include/spcl.h`` (``libspcl_b200.so``).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails,
+the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import pathlib
+import subprocess
+import threading
+
+_PKG_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "libspcl_b200.so"
+BUILD_SCRIPT = _PKG_DIR / "csrc" / "build.sh"
+
+MODE_NONE, MODE_HARD, MODE_SOFT = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+TILE = 128
+MAX_D = 256
+
+_c = ctypes
+_i64, _i32, _f32, _ptr = _c.c_int64, _c.c_int32, _c.c_float, _c.c_void_p
+
+# name -> argtypes; every entry point of include/spcl.h that returns an error code
+SIGNATURES = {
+    "spcl_l2norm_fwd": [_ptr, _ptr, _ptr, _c.c_int, _i64, _i64, _i64, _f32, _ptr],
+    "spcl_l2norm_bwd": [_ptr, _ptr, _ptr, _ptr, _c.c_int, _i64, _i64, _i64, _ptr],
+    "spcl_pack_views_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
+    "spcl_label_block_sig": [_ptr, _i64, _i64, _ptr, _ptr],
+    "spcl_supcon_fwd_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
+                             _ptr, _ptr],
+    "spcl_supcon_bwd_bf16": [_ptr, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _f32,
+                             _c.c_int, _ptr, _i64, _ptr],
+    "spcl_supcon_fwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _c.c_int, _ptr,
+                            _ptr, _ptr],
+    "spcl_supcon_bwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _f32, _f32,
+                            _c.c_int, _ptr, _i64, _ptr],
+    "spcl_supcon_finalize": [_ptr, _i64, _c.c_int, _ptr, _ptr],
+}
+OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error")
+ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SpclError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> pathlib.Path:
+    """Compile the CUDA sources for sm_100a into ``libspcl_b200.so`` (in-tree)."""
+    env = dict(os.environ)
+    res = subprocess.run(["bash", str(BUILD_SCRIPT)], capture_output=True, text=True, env=env)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise SpclError(f"building {LIB_PATH.name} failed (exit {res.returncode})")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not LIB_PATH.exists():
+                    raise SpclError(
+                        f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"(or bash {BUILD_SCRIPT}). spcl_b200 has no CPU/PyTorch fallback.")
+                handle = ctypes.CDLL(str(LIB_PATH))
+                for name, argtypes in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.argtypes = argtypes
+                    fn.restype = _c.c_int
+                handle.spcl_version.restype = _c.c_int
+                handle.spcl_error_string.argtypes = [_c.c_int]
+                handle.spcl_error_string.restype = _c.c_char_p
+                handle.spcl_last_cuda_error.restype = _c.c_char_p
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        h = lib()
+        msg = h.spcl_error_string(rc).decode()
+        if rc == -3:
+            msg += ": " + h.spcl_last_cuda_error().decode()
+        raise SpclError(f"{what} failed with code {rc}: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)

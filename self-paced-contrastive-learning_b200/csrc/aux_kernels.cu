@@ -1,0 +1,349 @@
+// HBM-bound helper kernels around the fused loss:
+//   * L2 normalise forward / backward      (contrastyou/projectors/nn.py:35-36, F.normalize(p=2, dim))
+//   * bf16 operand packing of the two views (replaces torch.cat at contrast_loss3.py:26)
+//   * per-128-anchor label signatures       (tile skipping for the tensor-core path)
+// Roofline: all three are pure streaming kernels; algorithmic bytes are stated in DESIGN.md.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <climits>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace spcl {
+
+static thread_local std::string g_last_cuda_error = "";
+
+void set_last_cuda_error(cudaError_t e, const char* where) {
+  g_last_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+
+namespace aux {
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T, int V> struct alignas(sizeof(T) * V) Vec { T v[V]; };
+
+// ------------------------------------------------------------------------------------------------
+// rows layout: x[rows][d], one warp per row, V elements (16 bytes) per lane per step
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) l2norm_rows_fwd(const T* __restrict__ x, T* __restrict__ y,
+                                                       float* __restrict__ inv_norm, int64_t rows, int d,
+                                                       float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
+    const T* xr = x + r * d;
+    float ss = 0.f;
+    for (int c = lane * V; c < d; c += 32 * V) {
+      const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xr + c);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { const float f = to_f(v.v[k]); ss = fmaf(f, f, ss); }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm != nullptr) inv_norm[r] = inv;
+    T* yr = y + r * d;
+    for (int c = lane * V; c < d; c += 32 * V) {
+      const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(xr + c);   // L1 hit: same warp just read it
+      Vec<T, V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = from_f<T>(to_f(v.v[k]) * inv);
+      *reinterpret_cast<Vec<T, V>*>(yr + c) = o;
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) l2norm_rows_bwd(const T* __restrict__ gy, const T* __restrict__ y,
+                                                       const float* __restrict__ inv_norm, T* __restrict__ gx,
+                                                       int64_t rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
+    const T* gr = gy + r * d;
+    const T* yr = y + r * d;
+    float dot = 0.f;
+    for (int c = lane * V; c < d; c += 32 * V) {
+      const Vec<T, V> a = *reinterpret_cast<const Vec<T, V>*>(gr + c);
+      const Vec<T, V> b = *reinterpret_cast<const Vec<T, V>*>(yr + c);
+#pragma unroll
+      for (int k = 0; k < V; ++k) dot = fmaf(to_f(a.v[k]), to_f(b.v[k]), dot);
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[r];
+    T* xr = gx + r * d;
+    for (int c = lane * V; c < d; c += 32 * V) {
+      const Vec<T, V> a = *reinterpret_cast<const Vec<T, V>*>(gr + c);
+      const Vec<T, V> b = *reinterpret_cast<const Vec<T, V>*>(yr + c);
+      Vec<T, V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = from_f<T>(inv * (to_f(a.v[k]) - to_f(b.v[k]) * dot));
+      *reinterpret_cast<Vec<T, V>*>(xr + c) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// strided layout: x[outer][d][inner] (NCHW with inner = H*W), one thread per V consecutive `inner`
+// positions, channel loop with stride `inner`; warps read V*32 consecutive elements per channel.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) l2norm_strided_fwd(const T* __restrict__ x, T* __restrict__ y,
+                                                          float* __restrict__ inv_norm, int64_t outer, int d,
+                                                          int64_t inner, float eps) {
+  const int64_t groups = inner / V;
+  const int64_t total = outer * groups;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t o = g / groups, s = (g % groups) * V;
+    const T* base = x + o * d * inner + s;
+    float ss[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) ss[k] = 0.f;
+    for (int c = 0; c < d; ++c) {
+      const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(base + c * inner);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { const float f = to_f(v.v[k]); ss[k] = fmaf(f, f, ss[k]); }
+    }
+    float inv[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      inv[k] = 1.f / fmaxf(sqrtf(ss[k]), eps);
+      if (inv_norm != nullptr) inv_norm[o * inner + s + k] = inv[k];
+    }
+    T* out = y + o * d * inner + s;
+    for (int c = 0; c < d; ++c) {
+      const Vec<T, V> v = *reinterpret_cast<const Vec<T, V>*>(base + c * inner);   // L2 hit
+      Vec<T, V> w;
+#pragma unroll
+      for (int k = 0; k < V; ++k) w.v[k] = from_f<T>(to_f(v.v[k]) * inv[k]);
+      *reinterpret_cast<Vec<T, V>*>(out + c * inner) = w;
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) l2norm_strided_bwd(const T* __restrict__ gy, const T* __restrict__ y,
+                                                          const float* __restrict__ inv_norm, T* __restrict__ gx,
+                                                          int64_t outer, int d, int64_t inner) {
+  const int64_t groups = inner / V;
+  const int64_t total = outer * groups;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t o = g / groups, s = (g % groups) * V;
+    const int64_t off = o * d * inner + s;
+    float dot[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) dot[k] = 0.f;
+    for (int c = 0; c < d; ++c) {
+      const Vec<T, V> a = *reinterpret_cast<const Vec<T, V>*>(gy + off + c * inner);
+      const Vec<T, V> b = *reinterpret_cast<const Vec<T, V>*>(y + off + c * inner);
+#pragma unroll
+      for (int k = 0; k < V; ++k) dot[k] = fmaf(to_f(a.v[k]), to_f(b.v[k]), dot[k]);
+    }
+    float inv[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) inv[k] = inv_norm[o * inner + s + k];
+    for (int c = 0; c < d; ++c) {
+      const Vec<T, V> a = *reinterpret_cast<const Vec<T, V>*>(gy + off + c * inner);
+      const Vec<T, V> b = *reinterpret_cast<const Vec<T, V>*>(y + off + c * inner);
+      Vec<T, V> w;
+#pragma unroll
+      for (int k = 0; k < V; ++k) w.v[k] = from_f<T>(inv[k] * (to_f(a.v[k]) - to_f(b.v[k]) * dot[k]));
+      *reinterpret_cast<Vec<T, V>*>(gx + off + c * inner) = w;
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline unsigned grid_for(int64_t threads_needed) {
+  int64_t blocks = ceil_div(threads_needed, 256);
+  const int64_t cap = 148LL * 16;     // 8 waves of 2 resident CTAs/SM is plenty for a streaming kernel
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+template <typename T>
+static int launch_fwd(const void* x, void* y, float* inv_norm, int64_t outer, int64_t d, int64_t inner, float eps,
+                      cudaStream_t s) {
+  constexpr int VMAX = 16 / sizeof(T);
+  const T* xp = static_cast<const T*>(x);
+  T* yp = static_cast<T*>(y);
+  const bool al = aligned16(x) && aligned16(y);
+  if (inner == 1) {
+    const unsigned grid = grid_for(outer * 32);
+    if (al && d % VMAX == 0) l2norm_rows_fwd<T, VMAX><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    else l2norm_rows_fwd<T, 1><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+  } else {
+    if (al && inner % VMAX == 0)
+      l2norm_strided_fwd<T, VMAX><<<grid_for(outer * inner / VMAX), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, inner, eps);
+    else
+      l2norm_strided_fwd<T, 1><<<grid_for(outer * inner), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, inner, eps);
+  }
+  SPCL_LAUNCH_CHECK("spcl_l2norm_fwd");
+  return SPCL_OK;
+}
+
+template <typename T>
+static int launch_bwd(const void* gy, const void* y, const float* inv_norm, void* gx, int64_t outer, int64_t d,
+                      int64_t inner, cudaStream_t s) {
+  constexpr int VMAX = 16 / sizeof(T);
+  const T* gp = static_cast<const T*>(gy);
+  const T* yp = static_cast<const T*>(y);
+  T* xp = static_cast<T*>(gx);
+  const bool al = aligned16(gy) && aligned16(y) && aligned16(gx);
+  if (inner == 1) {
+    const unsigned grid = grid_for(outer * 32);
+    if (al && d % VMAX == 0) l2norm_rows_bwd<T, VMAX><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    else l2norm_rows_bwd<T, 1><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+  } else {
+    if (al && inner % VMAX == 0)
+      l2norm_strided_bwd<T, VMAX><<<grid_for(outer * inner / VMAX), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d, inner);
+    else
+      l2norm_strided_bwd<T, 1><<<grid_for(outer * inner), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d, inner);
+  }
+  SPCL_LAUNCH_CHECK("spcl_l2norm_bwd");
+  return SPCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack: dst[r][0..d_pad) bf16 <- (r < n ? z1[r] : z2[r-n]), zero padded columns; 8 outputs / thread
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_views_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                         int64_t n, int d, int64_t ld1, int64_t ld2,
+                                                         __nv_bfloat16* __restrict__ dst, int d_pad, bool vec_ok) {
+  const int groups = d_pad >> 3;
+  const int64_t total = 2 * n * groups;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups;
+    const int c = static_cast<int>(g % groups) << 3;
+    const float* src = r < n ? z1 + r * ld1 : z2 + (r - n) * ld2;
+    float f[8];
+    if (vec_ok && c + 8 <= d) {
+      const float4 a = *reinterpret_cast<const float4*>(src + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + c + 4);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = (c + k) < d ? src[c + k] : 0.f;
+    }
+    Vec<__nv_bfloat162, 4> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<Vec<__nv_bfloat162, 4>*>(dst + r * d_pad + c) = o;
+  }
+}
+
+// one warp per 128-anchor block: {min label, max label, bloom lo, bloom hi}
+__global__ void __launch_bounds__(128) label_sig_kernel(const int32_t* __restrict__ labels, int64_t n_total,
+                                                        int64_t n_blocks, int4* __restrict__ sig) {
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (blk >= n_blocks) return;
+  int mn = INT_MAX, mx = INT_MIN;
+  unsigned lo = 0u, hi = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = blk * 128 + k * 32 + lane;
+    if (i < n_total) {
+      const int v = labels[i];
+      mn = min(mn, v);
+      mx = max(mx, v);
+      const unsigned h = (static_cast<unsigned>(v) * 0x9E3779B1u) >> 26;
+      if (h < 32) lo |= 1u << h; else hi |= 1u << (h - 32);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+  }
+  if (lane == 0) sig[blk] = make_int4(mn, mx, static_cast<int>(lo), static_cast<int>(hi));
+}
+
+}  // namespace aux
+}  // namespace spcl
+
+using namespace spcl;
+
+extern "C" int spcl_version(void) { return 100; }
+
+extern "C" const char* spcl_error_string(int code) {
+  switch (code) {
+    case SPCL_OK: return "ok";
+    case SPCL_ERR_INVALID_ARG: return "invalid argument (null pointer, bad shape, bad range or bad hyper-parameter)";
+    case SPCL_ERR_UNSUPPORTED: return "unsupported configuration for this build (see SPCL_MAX_D / alignment rules)";
+    case SPCL_ERR_CUDA: return "CUDA runtime error (see spcl_last_cuda_error)";
+    case SPCL_ERR_NO_DRIVER: return "CUDA driver entry point unavailable (no GPU / driver)";
+    default: return "unknown spcl error code";
+  }
+}
+
+extern "C" const char* spcl_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+extern "C" int spcl_l2norm_fwd(const void* x, void* y, float* inv_norm, int dtype, int64_t outer, int64_t d,
+                               int64_t inner, float eps, spcl_stream_t stream) {
+  if (x == nullptr || y == nullptr || outer <= 0 || d <= 0 || inner <= 0 || d > INT_MAX) return SPCL_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case SPCL_DTYPE_F32: return aux::launch_fwd<float>(x, y, inv_norm, outer, d, inner, eps, s);
+    case SPCL_DTYPE_BF16: return aux::launch_fwd<__nv_bfloat16>(x, y, inv_norm, outer, d, inner, eps, s);
+    case SPCL_DTYPE_F16: return aux::launch_fwd<__half>(x, y, inv_norm, outer, d, inner, eps, s);
+    default: return SPCL_ERR_INVALID_ARG;
+  }
+}
+
+extern "C" int spcl_l2norm_bwd(const void* gy, const void* y, const float* inv_norm, void* gx, int dtype,
+                               int64_t outer, int64_t d, int64_t inner, spcl_stream_t stream) {
+  if (gy == nullptr || y == nullptr || inv_norm == nullptr || gx == nullptr || outer <= 0 || d <= 0 || inner <= 0 ||
+      d > INT_MAX)
+    return SPCL_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case SPCL_DTYPE_F32: return aux::launch_bwd<float>(gy, y, inv_norm, gx, outer, d, inner, s);
+    case SPCL_DTYPE_BF16: return aux::launch_bwd<__nv_bfloat16>(gy, y, inv_norm, gx, outer, d, inner, s);
+    case SPCL_DTYPE_F16: return aux::launch_bwd<__half>(gy, y, inv_norm, gx, outer, d, inner, s);
+    default: return SPCL_ERR_INVALID_ARG;
+  }
+}
+
+extern "C" int spcl_pack_views_bf16(const float* z1, const float* z2, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
+                                    void* dst, int64_t d_pad, spcl_stream_t stream) {
+  if (z1 == nullptr || z2 == nullptr || dst == nullptr || n <= 0 || d <= 0 || ld1 < d || ld2 < d)
+    return SPCL_ERR_INVALID_ARG;
+  if (d_pad < d || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
+  if (!aux::aligned16(dst)) return SPCL_ERR_INVALID_ARG;
+  const bool vec_ok = aux::aligned16(z1) && aux::aligned16(z2) && ld1 % 4 == 0 && ld2 % 4 == 0;
+  const int64_t total = 2 * n * (d_pad / 8);
+  aux::pack_views_kernel<<<aux::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z1, z2, n, (int)d, ld1, ld2, static_cast<__nv_bfloat16*>(dst), (int)d_pad, vec_ok);
+  SPCL_LAUNCH_CHECK("spcl_pack_views_bf16");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
+                                    spcl_stream_t stream) {
+  if (labels == nullptr || sig == nullptr || n_total <= 0 || n_pad < n_total || n_pad % SPCL_TILE != 0)
+    return SPCL_ERR_INVALID_ARG;
+  const int64_t n_blocks = n_pad / SPCL_TILE;
+  const unsigned grid = static_cast<unsigned>(ceil_div(n_blocks * 32, 128));
+  aux::label_sig_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(labels, n_total, n_blocks,
+                                                                            reinterpret_cast<int4*>(sig));
+  SPCL_LAUNCH_CHECK("spcl_label_block_sig");
+  return SPCL_OK;
+}

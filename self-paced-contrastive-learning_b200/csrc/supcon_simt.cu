@@ -1,0 +1,364 @@
+// fp32 SIMT path of the fused self-paced SupCon loss (exact-parity mode).
+//
+// Same tiling idea as the tensor-core path -- the N x N similarity is produced tile by tile and
+// consumed in registers, never stored -- but with fp32 operands and fp32 FMA, so the result agrees
+// with the reference (contrastyou/losses/contrast_loss3.py, fp32 end to end) to fp32 rounding.
+// It also carries the tri-state `mask=` form (:128-131), which the tensor-core path does not.
+//
+//   forward : one CTA owns 64 anchor rows and sweeps all columns twice
+//             sweep 1: rowsum_i = sum_{j in M_i} exp(S_ij - 1/tau), c_i            (:180-182)
+//             sweep 2: sum_j P W LLH, sum_j P W with W from the final logD_i       (:184-197, :207-214)
+//   backward: one CTA owns 64 anchor rows; per column tile it forms
+//             T_ij = M_ij E_ij u_i - P_ij W_ij / c_i  +  (same with i <-> j)
+//             in shared memory and accumulates dZ_I += T_IJ Z_J in registers.
+#include "common.cuh"
+
+namespace spcl {
+namespace simt {
+
+constexpr int BM = 64, BN = 64, BK = 32, NT = 256;
+
+struct Args {
+  const float* z;
+  int64_t N;
+  int d;
+  int64_t ldz;
+  const int32_t* labels;
+  const uint8_t* tri;
+  int64_t nh;
+  int64_t row_begin, row_end;
+  float inv_tau, gamma, inv_gamma;
+  int mode;
+};
+
+struct Smem {
+  float a[BM][BK + 1];
+  float b[BN][BK + 1];
+};
+
+// P_ij / M_ij for one ordered pair (diagonal already excluded by the caller)
+__device__ __forceinline__ void pair_flags(const Args& p, int64_t gi, int64_t gj, int li, int lj, bool& pos,
+                                           bool& valid) {
+  if (p.tri != nullptr) {
+    const uint8_t v = p.tri[(gi % p.nh) * p.nh + (gj % p.nh)];
+    pos = (v == 1);
+    valid = (v <= 1);
+  } else {
+    pos = (li == lj);
+    valid = true;
+  }
+}
+
+// acc[a][b] = <z[i0 + ty*4 + a], z[j0 + tx + 16 b]>
+__device__ __forceinline__ void tile_dot(const Args& p, Smem& sm, int64_t i0, int64_t j0, float (&acc)[4][4]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  for (int k0 = 0; k0 < p.d; k0 += BK) {
+#pragma unroll
+    for (int t = 0; t < (BM * BK) / NT; ++t) {
+      const int idx = tid + t * NT;
+      const int r = idx / BK, k = idx % BK;
+      const int64_t gi = i0 + r, gj = j0 + r;
+      const bool kok = (k0 + k) < p.d;
+      sm.a[r][k] = (kok && gi < p.N) ? p.z[gi * p.ldz + k0 + k] : 0.f;
+      sm.b[r][k] = (kok && gj < p.N) ? p.z[gj * p.ldz + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float ra[4], rb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ra[a] = sm.a[ty * 4 + a][k];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) rb[b] = sm.b[tx + 16 * b][k];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ra[a], rb[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+}
+
+// sum over the 16 lanes that share a row (tx = lane & 15)
+__device__ __forceinline__ float row_sum16(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(NT) fwd_kernel(Args p, float4* __restrict__ row_stats, float* __restrict__ partials) {
+  __shared__ Smem sm;
+  __shared__ float red[3][BM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+
+  int64_t gi[4];
+  int li[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    gi[a] = i0 + ty * 4 + a;
+    li[a] = (p.labels != nullptr && gi[a] < p.N) ? p.labels[gi[a]] : 0;
+  }
+
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, spx[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][4];
+
+  // ---- sweep 1: denominators and positive counts ----
+  for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
+    tile_dot(p, sm, i0, j0, acc);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t gj = j0 + tx + 16 * b;
+      if (gj >= p.N) continue;
+      const int lj = p.labels != nullptr ? p.labels[gj] : 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (gi[a] == gj || gi[a] >= p.N) continue;
+        bool pos, valid;
+        pair_flags(p, gi[a], gj, li[a], lj, pos, valid);
+        const float s = acc[a][b] * p.inv_tau;
+        if (valid) rowsum[a] += expf(s - shift);
+        if (pos) {
+          cnt[a] += 1.f;
+          spx[a] += s;
+        }
+      }
+    }
+  }
+  float logD[4], wl[4], wp[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    rowsum[a] = row_sum16(rowsum[a]);
+    cnt[a] = row_sum16(cnt[a]);
+    spx[a] = row_sum16(spx[a]);
+    logD[a] = shift + logf(rowsum[a]);
+    wl[a] = spx[a] - cnt[a] * logD[a];   // mode NONE: sum_j P (S - logD)
+    wp[a] = cnt[a];
+  }
+
+  // ---- sweep 2: self-paced weighted sums (needs the final logD) ----
+  if (p.mode != SPCL_MODE_NONE) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) wl[a] = wp[a] = 0.f;
+    for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
+      tile_dot(p, sm, i0, j0, acc);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t gj = j0 + tx + 16 * b;
+        if (gj >= p.N) continue;
+        const int lj = p.labels != nullptr ? p.labels[gj] : 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (gi[a] == gj || gi[a] >= p.N) continue;
+          bool pos, valid;
+          pair_flags(p, gi[a], gj, li[a], lj, pos, valid);
+          if (!pos) continue;
+          const float llh = acc[a][b] * p.inv_tau - logD[a];
+          const float w = sp_weight(-llh, p.gamma, p.inv_gamma, p.mode);
+          wl[a] = fmaf(w, llh, wl[a]);
+          wp[a] += w;
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      wl[a] = row_sum16(wl[a]);
+      wp[a] = row_sum16(wp[a]);
+    }
+  }
+
+  // ---- per-row epilogue + block partial sums ----
+  if (tx == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = ty * 4 + a;
+      float l = 0.f, w = 0.f, c = 0.f;
+      if (gi[a] < p.row_end) {
+        const float invc = 1.f / cnt[a];          // c == 0 -> inf -> NaN loss, like the reference's 0/0
+        const float A = wp[a] * invc;
+        const float u = A * expf(shift - logD[a]);
+        row_stats[gi[a]] = make_float4(logD[a], invc, A, u);
+        l = wl[a] * invc;
+        w = wp[a];
+        c = cnt[a];
+      }
+      red[0][r] = l;
+      red[1][r] = w;
+      red[2][r] = c;
+    }
+  }
+  __syncthreads();
+  if (tid < 96) {
+    const int which = tid >> 5, lane = tid & 31;
+    float v = red[which][lane] + red[which][lane + 32];
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(&partials[which], v);
+  }
+}
+
+template <int DV>
+__global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float4* __restrict__ row_stats,
+                                                 const float* __restrict__ scalars,
+                                                 const float* __restrict__ grad_out, float* __restrict__ dz,
+                                                 int64_t lddz) {
+  __shared__ Smem sm;
+  __shared__ float ts[BM][BN + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+
+  int64_t gi[4];
+  int li[4];
+  float4 si[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    gi[a] = i0 + ty * 4 + a;
+    const bool ok = gi[a] < p.N;
+    li[a] = (p.labels != nullptr && ok) ? p.labels[gi[a]] : 0;
+    si[a] = ok ? row_stats[gi[a]] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  float dzacc[4][DV];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < DV; ++c) dzacc[a][c] = 0.f;
+
+  float acc[4][4];
+  for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
+    tile_dot(p, sm, i0, j0, acc);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int cj = tx + 16 * b;
+      const int64_t gj = j0 + cj;
+      const bool col_ok = gj < p.N;
+      const int lj = (p.labels != nullptr && col_ok) ? p.labels[gj] : 0;
+      const float4 sj = col_ok ? row_stats[gj] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float t = 0.f;
+        if (col_ok && gi[a] < p.N && gi[a] != gj) {
+          bool pos_ij, val_ij, pos_ji, val_ji;
+          pair_flags(p, gi[a], gj, li[a], lj, pos_ij, val_ij);
+          if (p.tri != nullptr) pair_flags(p, gj, gi[a], lj, li[a], pos_ji, val_ji);
+          else { pos_ji = pos_ij; val_ji = val_ij; }
+          const float s = acc[a][b] * p.inv_tau;
+          const float e = expf(s - shift);
+          if (val_ij) t = fmaf(e, si[a].w, t);
+          if (val_ji) t = fmaf(e, sj.w, t);
+          if (pos_ij) t -= sp_weight(si[a].x - s, p.gamma, p.inv_gamma, p.mode) * si[a].y;
+          if (pos_ji) t -= sp_weight(sj.x - s, p.gamma, p.inv_gamma, p.mode) * sj.y;
+        }
+        ts[ty * 4 + a][cj] = t;
+      }
+    }
+    __syncthreads();
+    const int jmax = static_cast<int>(min(static_cast<int64_t>(BN), p.N - j0));
+    for (int jj = 0; jj < jmax; ++jj) {
+      const float* zrow = p.z + (j0 + jj) * p.ldz;
+      float t[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) t[a] = ts[ty * 4 + a][jj];
+#pragma unroll
+      for (int c = 0; c < DV; ++c) {
+        const int col = tx + 16 * c;
+        const float zv = col < p.d ? zrow[col] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dzacc[a][c] = fmaf(t[a], zv, dzacc[a][c]);
+      }
+    }
+    __syncthreads();
+  }
+
+  const float coef = grad_out[0] * scalars[3] * p.inv_tau;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (gi[a] >= p.row_end) continue;
+    float* out = dz + (gi[a] - p.row_begin) * lddz;
+#pragma unroll
+    for (int c = 0; c < DV; ++c) {
+      const int col = tx + 16 * c;
+      if (col < p.d) out[col] = dzacc[a][c] * coef;
+    }
+  }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ partials, float n_total, int correct_grad,
+                                float* __restrict__ scalars) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float loss_sum = partials[0], wp = partials[1], pc = partials[2];
+  const float ratio = wp / pc;                       // 0/0 -> NaN, like mean() of an empty selection (:189)
+  const float scale = (correct_grad && ratio > 0.f) ? 1.f / ratio : 1.f;   // :199-201
+  scalars[0] = -(loss_sum / n_total) * scale;        // :197
+  scalars[1] = ratio;
+  scalars[2] = scale;
+  scalars[3] = scale / n_total;
+}
+
+static int check_common(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                        const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end, float inv_tau,
+                        float gamma, int mode) {
+  if (z == nullptr || n_total <= 0 || d <= 0 || ldz < d) return SPCL_ERR_INVALID_ARG;
+  if (d > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
+  if ((labels == nullptr) == (tri == nullptr)) return SPCL_ERR_INVALID_ARG;
+  if (tri != nullptr && n_half * 2 != n_total) return SPCL_ERR_INVALID_ARG;
+  if (row_begin < 0 || row_end > n_total || row_begin >= row_end) return SPCL_ERR_INVALID_ARG;
+  if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_SOFT) return SPCL_ERR_INVALID_ARG;
+  if (mode != SPCL_MODE_NONE && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
+  return SPCL_OK;
+}
+
+}  // namespace simt
+}  // namespace spcl
+
+using namespace spcl;
+
+extern "C" int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                                   const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end,
+                                   float inv_tau, float gamma, int mode, float* row_stats, float* partials,
+                                   spcl_stream_t stream) {
+  int rc = simt::check_common(z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
+  simt::fwd_kernel<<<grid, simt::NT, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, reinterpret_cast<float4*>(row_stats), partials);
+  SPCL_LAUNCH_CHECK("spcl_supcon_fwd_f32");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                                   const uint8_t* tri, int64_t n_half, const float* row_stats,
+                                   const float* scalars, const float* grad_out, int64_t row_begin,
+                                   int64_t row_end, float inv_tau, float gamma, int mode, float* dz, int64_t lddz,
+                                   spcl_stream_t stream) {
+  int rc = simt::check_common(z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d)
+    return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float4* st = reinterpret_cast<const float4*>(row_stats);
+  if (d <= 64) simt::bwd_kernel<4><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
+  else if (d <= 128) simt::bwd_kernel<8><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
+  else simt::bwd_kernel<16><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
+  SPCL_LAUNCH_CHECK("spcl_supcon_bwd_f32");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_finalize(const float* partials, int64_t n_total, int correct_grad, float* scalars,
+                                    spcl_stream_t stream) {
+  if (partials == nullptr || scalars == nullptr || n_total <= 0) return SPCL_ERR_INVALID_ARG;
+  simt::finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, static_cast<float>(n_total),
+                                                                        correct_grad, scalars);
+  SPCL_LAUNCH_CHECK("spcl_supcon_finalize");
+  return SPCL_OK;
+}

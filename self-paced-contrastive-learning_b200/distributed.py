@@ -1,0 +1,148 @@
+"""Row-sharded self-paced SupCon over the GPUs of one box.
+
+The reference is single-process; this is additive.  Every rank holds the two views of its own
+samples (``z1``, ``z2``: ``[n_loc, d]``) and owns the anchor rows of those samples against ALL
+columns:
+
+  forward : pack local operands -> all-gather Z (bf16) and the labels -> fused forward on the owned
+            rows -> all-reduce of the three partial sums -> loss / ratio / scale on every rank;
+            all-gather of the per-row statistics for the backward.
+  backward: fused backward on the owned rows.  T = dS + dS^T is formed per tile from both blocks'
+            statistics, so each rank ends with exactly the gradient rows of its own embeddings:
+            no reduce-scatter of gradients is needed.
+
+Global anchor order is (rank, view, sample); the loss does not depend on the anchor order because
+positives are defined by label equality.  The result equals the single-GPU loss on the
+concatenated batch (checked in tests/test_distributed_*.py).
+
+The collectives go through ``torch.distributed`` (NCCL over NVLink on the box, gloo in the CPU
+tests).  The compute calls go through a small backend object so that the CPU tests can exercise
+this plumbing with the oracle standing in for the kernels; the product backend is CUDA-only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _native as nat
+from .ops import _ptr, _stream, pad_to
+
+__all__ = ["sharded_supcon_loss", "NativeBackend", "ShardPlan"]
+
+
+class ShardPlan:
+    """Where this rank's anchors live in the global (rank, view, sample) order."""
+
+    def __init__(self, n_loc: int, world: int, rank: int):
+        self.n_loc, self.world, self.rank = n_loc, world, rank
+        self.rows_loc = 2 * n_loc
+        self.N = self.rows_loc * world
+        self.row_begin = rank * self.rows_loc
+        self.row_end = self.row_begin + self.rows_loc
+
+
+class NativeBackend:
+    """CUDA kernels behind the C ABI (tensor-core path)."""
+
+    name = "bf16"
+
+    def check(self, plan: ShardPlan, d: int):
+        if plan.rows_loc % nat.TILE != 0:
+            raise nat.SpclError(f"row sharding needs 2 * n_local ({plan.rows_loc}) to be a multiple of {nat.TILE}")
+        if d > nat.MAX_D:
+            raise nat.SpclError(f"embedding width {d} > {nat.MAX_D}")
+
+    def pack(self, z1: Tensor, z2: Tensor) -> Tensor:
+        n, d = z1.shape
+        d_pad = pad_to(d, 64)
+        out = torch.empty(2 * n, d_pad, dtype=torch.bfloat16, device=z1.device)
+        nat.call("spcl_pack_views_bf16", _ptr(z1), _ptr(z2), n, d, z1.stride(0), z2.stride(0), _ptr(out), d_pad,
+                 _stream(z1))
+        return out
+
+    def forward_rows(self, z_all, labels_all, plan: ShardPlan, inv_tau, gamma, mode):
+        N, d_pad = z_all.shape
+        dev = z_all.device
+        st = _stream(z_all)
+        sig = torch.empty(N // nat.TILE, 4, dtype=torch.int32, device=dev)
+        nat.call("spcl_label_block_sig", _ptr(labels_all), N, N, _ptr(sig), st)
+        acc = torch.empty(N, 4, dtype=torch.float32, device=dev)
+        row_stats = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        partials = torch.zeros(3, dtype=torch.float32, device=dev)
+        nat.call("spcl_supcon_fwd_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig), plan.row_begin,
+                 plan.row_end, inv_tau, gamma, mode, _ptr(acc), _ptr(row_stats), _ptr(partials), st)
+        return row_stats[plan.row_begin:plan.row_end].contiguous(), partials, sig
+
+    def finalize(self, partials, N, correct_grad):
+        scalars = torch.empty(4, dtype=torch.float32, device=partials.device)
+        nat.call("spcl_supcon_finalize", _ptr(partials), N, int(correct_grad), _ptr(scalars), _stream(partials))
+        return scalars
+
+    def backward_rows(self, z_all, labels_all, sig, row_stats_all, scalars, grad, plan: ShardPlan, inv_tau, gamma,
+                      mode, d):
+        N, d_pad = z_all.shape
+        dz = torch.empty(plan.rows_loc, d, dtype=torch.float32, device=z_all.device)
+        nat.call("spcl_supcon_bwd_bf16", _ptr(z_all), N, N, d_pad, d, _ptr(labels_all), _ptr(sig),
+                 _ptr(row_stats_all), _ptr(scalars), _ptr(grad), plan.row_begin, plan.row_end, inv_tau, gamma, mode,
+                 _ptr(dz), dz.stride(0), _stream(z_all))
+        return dz
+
+
+def _gather_rows(local: Tensor, world: int, group) -> Tensor:
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+class _ShardedSupCon(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, labels, temperature, gamma, mode, correct_grad, group, backend):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n_loc, d = z1.shape
+        plan = ShardPlan(n_loc, world, rank)
+        backend.check(plan, d)
+        inv_tau = 1.0 / float(temperature)
+        z_loc = backend.pack(z1.contiguous(), z2.contiguous())
+        z_all = _gather_rows(z_loc, world, group)                       # N * d_pad * 2 B over NVLink
+        labels_all = _gather_rows(torch.cat([labels, labels]), world, group)
+        stats_loc, partials, sig = backend.forward_rows(z_all, labels_all, plan, inv_tau, float(gamma), int(mode))
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)    # 3 floats
+        scalars = backend.finalize(partials, plan.N, bool(correct_grad))
+        stats_all = _gather_rows(stats_loc, world, group)               # 16 B per anchor
+        ctx.save_for_backward(z_all, labels_all, sig, stats_all, scalars)
+        ctx.meta = (plan, inv_tau, float(gamma), int(mode), d, backend)
+        ctx.mark_non_differentiable(scalars)
+        return scalars[0].clone(), scalars
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_scalars):
+        z_all, labels_all, sig, stats_all, scalars = ctx.saved_tensors
+        plan, inv_tau, gamma, mode, d, backend = ctx.meta
+        g = g_loss.reshape(1).to(torch.float32).contiguous()
+        dz = backend.backward_rows(z_all, labels_all, sig, stats_all, scalars, g, plan, inv_tau, gamma, mode, d)
+        n = plan.n_loc
+        return dz[:n], dz[n:], None, None, None, None, None, None, None
+
+
+def sharded_supcon_loss(z1: Tensor, z2: Tensor, labels: Tensor, *, temperature: float = 0.07, gamma: float = 1e6,
+                        mode: int = nat.MODE_NONE, correct_grad: bool = False, group=None,
+                        backend: Optional[object] = None):
+    """Loss over the union of all ranks' anchors; ``labels`` are int32 ids consistent across ranks.
+
+    -> (loss 0-d differentiable w.r.t. the local z1 / z2, scalars[4] = loss, ratio, scale, scale/N).
+    Every rank must pass the same ``n_loc``.  The gradient returned to each rank is the gradient of the
+    GLOBAL loss w.r.t. its local embeddings (what the single-GPU run would give for those rows).
+    """
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    if backend is None:
+        if not z1.is_cuda:
+            raise RuntimeError("spcl_b200 runs on CUDA tensors only: there is no CPU path")
+        backend = NativeBackend()
+    if labels.dtype != torch.int32:
+        raise TypeError("labels must be int32 and globally consistent across ranks")
+    return _ShardedSupCon.apply(z1, z2, labels, temperature, gamma, mode, correct_grad, group, backend)

@@ -1,0 +1,226 @@
+"""Drop-in loss modules with the reference's surface.
+
+Mirrors ``contrastyou/losses/contrast_loss3.py``: ``SupConLoss1`` (:34-110) and
+``SelfPacedSupConLoss`` (:113-222) -- same constructor arguments, same
+``forward(proj_feat1, proj_feat2, target=None, mask=None)`` precedence (mask > target > SimCLR
+identity, :128-143), ``set_gamma`` / ``age_param`` (:216-222), ``downgrade_ratio`` (:191) and the
+diagnostic attributes the hooks read (``sim_exp``, ``sim_logits``, ``pos_mask``, ``neg_mask``,
+``sp_mask``; ``semi_seg/hooks/infonce.py:185-187, :263``).  The arithmetic runs in the fused CUDA
+kernels behind ``spcl::supcon_fwd`` / ``spcl::supcon_bwd``; nothing N x N is stored unless one of
+the diagnostic attributes is actually read.
+
+Extra keyword arguments (accepted through the reference's ``**kwargs``):
+
+``precision``   "auto" (default) | "bf16" | "fp32".  bf16 = tcgen05 tensor-core kernels, fp32 = SIMT
+                kernels that match the reference to fp32 rounding.  "auto" takes fp32 for the
+                tri-state ``mask=`` form and for N < 1024 (the reference's own batch sizes), bf16
+                above.
+``check_nan``   True (default) raises ``RuntimeError`` on a NaN loss right away like the reference
+                (:203-204), which costs one host sync per call; False leaves the check to the caller.
+``validate``    True (default) keeps the reference's ``assert is_normalized`` (:154), active only
+                when Python runs without ``-O``, exactly like the reference.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _native as nat
+from . import ops
+
+__all__ = ["SupConLoss1", "SelfPacedSupConLoss", "supcon_loss", "is_normalized"]
+
+_AUTO_TC_MIN_N = 1024
+_DIAG_MAX_N = 16384
+
+
+def is_normalized(feature: Tensor, dim: int = 1) -> bool:
+    """contrast_loss3.py:20-22."""
+    norms = feature.norm(dim=dim)
+    return bool(torch.allclose(norms, torch.ones_like(norms)))
+
+
+def _pick_tc(precision: str, N: int, has_tri: bool) -> bool:
+    if precision == "bf16":
+        return True
+    if precision == "fp32":
+        return False
+    if precision != "auto":
+        raise ValueError(f"precision must be 'auto', 'bf16' or 'fp32', got {precision!r}")
+    return (not has_tri) and N >= _AUTO_TC_MIN_N
+
+
+class _Diagnostics:
+    """Lazily materialised N x N views of the last call (what the reference stashes at :175-178, :188)."""
+
+    def __init__(self, z1, z2, labels, tri, row_stats, temperature, gamma, mode):
+        self.z1, self.z2, self.labels, self.tri = z1.detach(), z2.detach(), labels, tri
+        self.row_stats, self.t, self.gamma, self.mode = row_stats, temperature, gamma, mode
+        self._cache = {}
+
+    def _base(self):
+        if "logits" not in self._cache:
+            n = self.z1.shape[0]
+            if 2 * n > _DIAG_MAX_N:
+                raise RuntimeError(f"diagnostic N x N matrices are only materialised for N <= {_DIAG_MAX_N}")
+            z = torch.cat([self.z1, self.z2]).float()
+            logits = (z @ z.t()) / self.t
+            logits = logits - logits.max()
+            keep = 1.0 - torch.eye(2 * n, device=z.device)
+            if self.tri is not None:
+                t = self.tri.repeat(2, 2)
+                pos, neg = (t == 1).float() * keep, (t == 0).float() * keep
+            else:
+                lab = torch.cat([self.labels, self.labels])
+                same = lab[:, None] == lab[None, :]
+                pos, neg = same.float() * keep, (~same).float() * keep
+            self._cache.update(logits=logits, pos=pos, neg=neg)
+        return self._cache
+
+    def get(self, name):
+        c = self._base()
+        if name == "sim_logits":
+            return c["logits"]
+        if name == "sim_exp":
+            return torch.exp(c["logits"])
+        if name == "pos_mask":
+            return c["pos"]
+        if name == "neg_mask":
+            return c["neg"]
+        if name == "sp_mask":
+            N = c["pos"].shape[0]
+            z = torch.cat([self.z1, self.z2]).float()
+            llh = (z @ z.t()) / self.t - self.row_stats[:N, 0:1]
+            l = -llh
+            if self.mode == nat.MODE_NONE:
+                w = torch.ones_like(l)
+            elif self.mode == nat.MODE_HARD:
+                w = (l <= self.gamma).float()
+            else:
+                w = torch.clamp_min(1 - l / self.gamma, 0)
+            return torch.maximum(w, 1 - c["pos"])
+        raise AttributeError(name)
+
+
+def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Optional[Tensor] = None,
+                temperature: float = 0.07, gamma: float = 1e6, mode: int = nat.MODE_NONE,
+                correct_grad: bool = False, precision: str = "auto"):
+    """Functional form.  -> (loss 0-d, scalars[4] = loss/ratio/scale/scale_over_N, aux dict)."""
+    if proj_feat1.shape != proj_feat2.shape:
+        raise AssertionError((proj_feat1.shape, proj_feat2.shape))
+    if not (proj_feat1.is_cuda and proj_feat2.is_cuda):
+        raise RuntimeError("spcl_b200 runs on CUDA tensors only: there is no CPU path (got "
+                           f"{proj_feat1.device} / {proj_feat2.device})")
+    n = proj_feat1.shape[0]
+    dev = proj_feat2.device
+    z1 = proj_feat1.float()
+    z2 = proj_feat2.float()
+    labels = tri = None
+    if mask is not None:                      # :128-131
+        tri = ops.tri_codes(mask, n, dev)
+    elif target is not None:                  # :133-139
+        labels = ops.label_codes(target, n, dev)
+    else:                                     # :140-143  SimCLR
+        labels = torch.arange(n, dtype=torch.int32, device=dev)
+    use_tc = _pick_tc(precision, 2 * n, tri is not None)
+    scalars, row_stats, _, _, _ = ops.supcon_fwd(z1, z2, labels, tri, float(temperature), float(gamma), int(mode),
+                                                 bool(correct_grad), use_tc)
+    return scalars[0], scalars, dict(labels=labels, tri=tri, row_stats=row_stats, use_tc=use_tc)
+
+
+class _FusedSupConBase(nn.Module):
+    _mode = nat.MODE_NONE
+
+    def _init_common(self, temperature, kwargs):
+        self._t = temperature
+        self._precision = kwargs.pop("precision", "auto")
+        self._check_nan = bool(kwargs.pop("check_nan", True))
+        self._validate = bool(kwargs.pop("validate", True))
+        self._diag = None
+        self._scalars = None
+        self._ratio_cache = None
+
+    def _gamma_mode_cg(self):
+        raise NotImplementedError
+
+    def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None, **kwargs):
+        if mask is not None:
+            assert mask.shape == torch.Size([proj_feat1.size(0)] * 2), mask.shape
+        if self._validate:
+            assert is_normalized(proj_feat1) and is_normalized(proj_feat2), "features need to be normalized first"
+        assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
+        gamma, mode, cg = self._gamma_mode_cg()
+        loss, scalars, aux = supcon_loss(proj_feat1, proj_feat2, target=target, mask=mask, temperature=self._t,
+                                         gamma=gamma, mode=mode, correct_grad=cg, precision=self._precision)
+        self._scalars = scalars.detach()
+        self._ratio_cache = None
+        self._diag = _Diagnostics(proj_feat1, proj_feat2, aux["labels"], aux["tri"], aux["row_stats"], self._t,
+                                  gamma, mode)
+        if self._check_nan and torch.isnan(loss):      # :203-204 (one host sync, as in the reference)
+            raise RuntimeError(loss)
+        return loss
+
+    # diagnostics the hooks read after every call; materialised only on access
+    def _diag_get(self, name):
+        if self._diag is None:
+            raise AttributeError(f"{name} is only available after a forward call")
+        return self._diag.get(name)
+
+    sim_exp = property(lambda self: self._diag_get("sim_exp"))
+    sim_logits = property(lambda self: self._diag_get("sim_logits"))
+    pos_mask = property(lambda self: self._diag_get("pos_mask"))
+    neg_mask = property(lambda self: self._diag_get("neg_mask"))
+
+
+class SupConLoss1(_FusedSupConBase):
+    """contrast_loss3.py:34-110 (W == 1)."""
+
+    def __init__(self, temperature=0.07, exclude_other_pos=False, **kwargs):
+        super().__init__()
+        if exclude_other_pos:
+            # :97-100; default off and never enabled by any caller (infonce.py:93) -- SURVEY.md section 8 row f3
+            raise NotImplementedError("exclude_other_pos=True is not implemented in the fused kernels yet")
+        self._init_common(temperature, kwargs)
+        self._exclude_pos = False
+
+    def _gamma_mode_cg(self):
+        return 1e6, nat.MODE_NONE, False
+
+
+class SelfPacedSupConLoss(_FusedSupConBase):
+    """contrast_loss3.py:113-222."""
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} with T: {self._t}, method: {self._weight_update} gamma: {self.__gamma}"
+
+    def __init__(self, temperature=0.07, weight_update="hard", correct_grad=False, **kwargs):
+        super().__init__()
+        self._init_common(temperature, kwargs)
+        self._weight_update = weight_update
+        self.__gamma = 1e6
+        self._correct_grad = correct_grad
+
+    def _gamma_mode_cg(self):
+        # every value other than "hard" selects the soft rule in the reference (:210-213)
+        mode = nat.MODE_HARD if self._weight_update == "hard" else nat.MODE_SOFT
+        return self.__gamma, mode, bool(self._correct_grad)
+
+    def set_gamma(self, gamma):
+        self.__gamma = float(gamma)
+
+    @property
+    def age_param(self):
+        return self.__gamma
+
+    @property
+    def downgrade_ratio(self):
+        """mean of W over the positive pairs of the last call (:189-191); read lazily (one sync)."""
+        if self._scalars is None:
+            raise AttributeError("downgrade_ratio is only available after a forward call")
+        if self._ratio_cache is None:
+            self._ratio_cache = float(self._scalars[1].item())
+        return self._ratio_cache
+
+    sp_mask = property(lambda self: self._diag_get("sp_mask"))

@@ -1,0 +1,280 @@
+"""torch custom ops over the C ABI (``include/spcl.h``).
+
+``spcl::supcon_fwd`` / ``spcl::supcon_bwd`` are the fused self-paced SupCon forward / backward
+(reference: ``contrastyou/losses/contrast_loss3.py:25-31, :147-214`` and their autograd),
+``spcl::l2norm_fwd`` / ``spcl::l2norm_bwd`` the projector's normalise tail
+(``contrastyou/projectors/nn.py:35-36``).  PyTorch is used for device memory, streams and autograd
+plumbing only; all arithmetic on the path happens in ``libspcl_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as nat
+
+__all__ = ["supcon_fwd", "supcon_bwd", "l2norm_fwd", "l2norm_bwd", "pad_to", "label_codes", "tri_codes"]
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def pad_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _require_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("spcl_b200 ops run on CUDA tensors only (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+# --------------------------------------------------------------------------------------------------
+# label handling (host side of contrast_loss3.py:133-139)
+# --------------------------------------------------------------------------------------------------
+def label_codes(target, n: int, device) -> Tensor:
+    """int32[n] codes whose equality classes equal the reference's ``torch.eq`` on ``target``.
+
+    python lists go through float32 in the reference (``torch.Tensor(list)``, :135); integers below
+    2**24 are exact there, so they are used as they are; anything else is mapped to its float32
+    equality classes.  Tensors are compared in their own dtype (:136).
+    """
+    import numpy as np
+
+    if isinstance(target, (list, tuple)):
+        arr = np.asarray(target)
+        if arr.ndim != 1 or arr.shape[0] != n:
+            raise AssertionError((arr.shape, n))
+        if arr.dtype.kind in "iub" and (arr.size == 0 or np.abs(arr).max() < 2 ** 24):
+            codes = arr.astype(np.int32)
+        else:
+            _, inv = np.unique(arr.astype(np.float32), return_inverse=True)
+            codes = inv.astype(np.int32)
+        return torch.from_numpy(codes).to(device, non_blocking=True)
+    if not isinstance(target, Tensor):
+        raise TypeError(f"target must be a list or a Tensor, got {type(target)}")
+    if target.dim() != 1 or target.shape[0] != n:
+        raise AssertionError((tuple(target.shape), n))
+    t = target.to(device)
+    if t.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8, torch.bool):
+        return t.to(torch.int32)
+    # int64 / floating labels: exact equality classes (this path synchronises; pass int32 to avoid it)
+    _, inv = torch.unique(t, return_inverse=True)
+    return inv.to(torch.int32)
+
+
+def tri_codes(mask: Tensor, n: int, device) -> Tensor:
+    """uint8[n, n]: 1 = positive (mask == 1), 0 = negative (mask == 0), 2 = ignored (:130-131)."""
+    if tuple(mask.shape) != (n, n):
+        raise AssertionError((tuple(mask.shape), n))
+    m = mask.to(device)
+    out = torch.full((n, n), 2, dtype=torch.uint8, device=device)
+    out[m == 0] = 0
+    out[m == 1] = 1
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fused loss
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("spcl::supcon_fwd", mutates_args=(), device_types="cuda")
+def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[Tensor], temperature: float,
+               gamma: float, mode: int, correct_grad: bool, use_tc: bool
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (scalars[4] = loss, ratio, scale, scale/N ; row_stats[n_pad, 4] ; packed operands ;
+    labels_full int32[n_pad] ; block signatures int32[n_pad/128, 4])."""
+    _require_cuda(z1, z2, labels, tri)
+    if z1.shape != z2.shape or z1.dim() != 2:
+        raise AssertionError((tuple(z1.shape), tuple(z2.shape)))
+    if z1.dtype != torch.float32 or z2.dtype != torch.float32:
+        raise TypeError("spcl::supcon_fwd takes float32 anchors")
+    n, d = z1.shape
+    N = 2 * n
+    if d > nat.MAX_D:
+        raise nat.SpclError(f"embedding width {d} > {nat.MAX_D} is not supported by this build")
+    if (labels is None) == (tri is None):
+        raise ValueError("exactly one of labels / tri must be given")
+    if tri is not None and use_tc:
+        raise nat.SpclError("the tri-state mask= form runs on the fp32 path only (precision='fp32' or 'auto')")
+    dev = z1.device
+    z1 = z1.contiguous()
+    z2 = z2.contiguous()
+    n_pad = pad_to(N, nat.TILE)
+    st = _stream(z1)
+    inv_tau = 1.0 / float(temperature)
+    row_stats = torch.zeros(n_pad, 4, dtype=torch.float32, device=dev)
+    partials = torch.zeros(3, dtype=torch.float32, device=dev)
+    scalars = torch.empty(4, dtype=torch.float32, device=dev)
+
+    if labels is not None:
+        if labels.dtype != torch.int32 or labels.shape != (n,):
+            raise TypeError("labels must be int32[n]")
+        labels_full = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+        labels_full[:n] = labels
+        labels_full[n:N] = labels
+    else:
+        labels_full = torch.empty(0, dtype=torch.int32, device=dev)
+
+    if use_tc:
+        d_pad = pad_to(d, 64)
+        zpack = torch.zeros(n_pad, d_pad, dtype=torch.bfloat16, device=dev)
+        nat.call("spcl_pack_views_bf16", _ptr(z1), _ptr(z2), n, d, z1.stride(0), z2.stride(0), _ptr(zpack),
+                 d_pad, st)
+        sig = torch.empty(n_pad // nat.TILE, 4, dtype=torch.int32, device=dev)
+        nat.call("spcl_label_block_sig", _ptr(labels_full), N, n_pad, _ptr(sig), st)
+        acc = torch.empty(n_pad, 4, dtype=torch.float32, device=dev)
+        nat.call("spcl_supcon_fwd_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), 0, N,
+                 inv_tau, float(gamma), int(mode), _ptr(acc), _ptr(row_stats), _ptr(partials), st)
+    else:
+        zpack = torch.cat([z1, z2], dim=0)
+        sig = torch.empty(0, 4, dtype=torch.int32, device=dev)
+        nat.call("spcl_supcon_fwd_f32", _ptr(zpack), N, d, zpack.stride(0),
+                 _ptr(labels_full) if labels is not None else None, _ptr(tri), n, 0, N, inv_tau, float(gamma),
+                 int(mode), _ptr(row_stats), _ptr(partials), st)
+    nat.call("spcl_supcon_finalize", _ptr(partials), N, int(bool(correct_grad)), _ptr(scalars), st)
+    return scalars, row_stats, zpack, labels_full, sig
+
+
+@supcon_fwd.register_fake
+def _(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc):
+    n, d = z1.shape
+    n_pad = pad_to(2 * n, nat.TILE)
+    scalars = z1.new_empty(4)
+    row_stats = z1.new_empty(n_pad, 4)
+    if use_tc:
+        zpack = z1.new_empty(n_pad, pad_to(d, 64), dtype=torch.bfloat16)
+        sig = z1.new_empty(n_pad // nat.TILE, 4, dtype=torch.int32)
+    else:
+        zpack = z1.new_empty(2 * n, d)
+        sig = z1.new_empty(0, 4, dtype=torch.int32)
+    labels_full = z1.new_empty(n_pad if labels is not None else 0, dtype=torch.int32)
+    return scalars, row_stats, zpack, labels_full, sig
+
+
+@torch.library.custom_op("spcl::supcon_bwd", mutates_args=(), device_types="cuda")
+def supcon_bwd(grad_loss: Tensor, zpack: Tensor, labels_full: Tensor, sig: Tensor, tri: Optional[Tensor],
+               row_stats: Tensor, scalars: Tensor, temperature: float, gamma: float, mode: int, use_tc: bool,
+               n: int, d: int) -> Tensor:
+    """-> dZ float32 [2n, d] (rows [0, n) belong to view 1, [n, 2n) to view 2)."""
+    _require_cuda(grad_loss, zpack, row_stats, scalars)
+    N = 2 * n
+    dev = zpack.device
+    st = _stream(zpack)
+    inv_tau = 1.0 / float(temperature)
+    g = grad_loss.reshape(1).to(torch.float32).contiguous()
+    dz = torch.empty(N, d, dtype=torch.float32, device=dev)
+    if use_tc:
+        n_pad, d_pad = zpack.shape
+        nat.call("spcl_supcon_bwd_bf16", _ptr(zpack), N, n_pad, d_pad, d, _ptr(labels_full), _ptr(sig),
+                 _ptr(row_stats), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz),
+                 dz.stride(0), st)
+    else:
+        nat.call("spcl_supcon_bwd_f32", _ptr(zpack), N, d, zpack.stride(0),
+                 _ptr(labels_full) if tri is None else None, _ptr(tri), n, _ptr(row_stats), _ptr(scalars),
+                 _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz), dz.stride(0), st)
+    return dz
+
+
+@supcon_bwd.register_fake
+def _(grad_loss, zpack, labels_full, sig, tri, row_stats, scalars, temperature, gamma, mode, use_tc, n, d):
+    return row_stats.new_empty(2 * n, d)
+
+
+def _supcon_setup(ctx, inputs, output):
+    z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc = inputs
+    scalars, row_stats, zpack, labels_full, sig = output
+    ctx.save_for_backward(zpack, labels_full, sig, tri, row_stats, scalars)
+    ctx.hp = (temperature, gamma, mode, use_tc, z1.shape[0], z1.shape[1])
+    ctx.set_materialize_grads(False)
+
+
+def _supcon_backward(ctx, g_scalars, g_stats, g_zpack, g_labels, g_sig):
+    if g_scalars is None:
+        return (None,) * 9
+    zpack, labels_full, sig, tri, row_stats, scalars = ctx.saved_tensors
+    temperature, gamma, mode, use_tc, n, d = ctx.hp
+    # only d loss / d z is defined; ratio / scale are constants of the step (the reference detaches them)
+    dz = supcon_bwd(g_scalars[0], zpack, labels_full, sig, tri, row_stats, scalars, temperature, gamma, mode,
+                    use_tc, n, d)
+    return dz[:n], dz[n:], None, None, None, None, None, None, None
+
+
+supcon_fwd.register_autograd(_supcon_backward, setup_context=_supcon_setup)
+
+
+# --------------------------------------------------------------------------------------------------
+# L2 normalise
+# --------------------------------------------------------------------------------------------------
+_DTYPES = {torch.float32: nat.DTYPE_F32, torch.bfloat16: nat.DTYPE_BF16, torch.float16: nat.DTYPE_F16}
+
+
+def _odi(shape, dim: int):
+    dim = dim % len(shape)
+    return math.prod(shape[:dim]), shape[dim], math.prod(shape[dim + 1:])
+
+
+@torch.library.custom_op("spcl::l2norm_fwd", mutates_args=(), device_types="cuda")
+def l2norm_fwd(x: Tensor, dim: int, eps: float) -> Tuple[Tensor, Tensor]:
+    _require_cuda(x)
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {x.dtype}")
+    x = x.contiguous()
+    outer, d, inner = _odi(x.shape, dim)
+    y = torch.empty_like(x)
+    inv = torch.empty(outer * inner, dtype=torch.float32, device=x.device)
+    if x.numel():
+        nat.call("spcl_l2norm_fwd", _ptr(x), _ptr(y), _ptr(inv), _DTYPES[x.dtype], outer, d, inner, float(eps),
+                 _stream(x))
+    return y, inv
+
+
+@l2norm_fwd.register_fake
+def _(x, dim, eps):
+    outer, d, inner = _odi(x.shape, dim)
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty(outer * inner,
+                                                                                   dtype=torch.float32)
+
+
+@torch.library.custom_op("spcl::l2norm_bwd", mutates_args=(), device_types="cuda")
+def l2norm_bwd(gy: Tensor, y: Tensor, inv_norm: Tensor, dim: int) -> Tensor:
+    _require_cuda(gy, y, inv_norm)
+    gy = gy.contiguous().to(y.dtype)
+    outer, d, inner = _odi(y.shape, dim)
+    gx = torch.empty_like(y)
+    if y.numel():
+        nat.call("spcl_l2norm_bwd", _ptr(gy), _ptr(y), _ptr(inv_norm), _ptr(gx), _DTYPES[y.dtype], outer, d, inner,
+                 _stream(y))
+    return gx
+
+
+@l2norm_bwd.register_fake
+def _(gy, y, inv_norm, dim):
+    return torch.empty_like(y)
+
+
+def _l2_setup(ctx, inputs, output):
+    _, dim, _ = inputs
+    y, inv = output
+    ctx.save_for_backward(y, inv)
+    ctx.dim = dim
+    ctx.set_materialize_grads(False)
+
+
+def _l2_backward(ctx, gy, g_inv):
+    if gy is None:
+        return None, None, None
+    y, inv = ctx.saved_tensors
+    return l2norm_bwd(gy, y, inv, ctx.dim), None, None
+
+
+l2norm_fwd.register_autograd(_l2_backward, setup_context=_l2_setup)

@@ -1,0 +1,328 @@
+"""Parity of the CUDA paths against the oracle / the reference's golden vectors (B200 only)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import spcl_b200
+from spcl_b200 import _native as nat
+from spcl_b200.workloads import acdc_meta_labels, make_views, make_workload
+from oracle.closed_form import supcon_closed_form
+from oracle.dense_port import dense_supcon
+from conftest import Golden, parse_cfg1_case
+from torch_ref import supcon_ref64
+
+pytestmark = pytest.mark.gpu
+
+CFG1 = Golden("cfg1_n64_d128.npz")
+TINY = Golden("tiny_n5_d16.npz")
+CFG2 = Golden("cfg2_n256_d256.npz")
+MODE = {"none": nat.MODE_NONE, "hard": nat.MODE_HARD, "soft": nat.MODE_SOFT}
+
+# ---- stated tolerances -------------------------------------------------------------------------
+# fp32 SIMT path vs the fp32 reference: both round in fp32, only the summation order differs.
+FP32_LOSS_RTOL, FP32_GRAD_REL = 2e-5, 1e-4
+# bf16 tensor-core path vs the fp64 oracle evaluated on the SAME bf16-rounded operands: remaining error is
+# ex2.approx (2^-22), fp32 accumulation order and the bf16 rounding of T before the second MMA (2^-9 per term).
+BF16_TIGHT_LOSS_RTOL, BF16_TIGHT_GRAD_REL, BF16_TIGHT_COS = 3e-4, 2e-2, 0.9999
+# bf16 path vs the fp32 reference on raw fp32 inputs: adds the operand quantisation (|ds| <= 2^-8/tau).
+BF16_LOOSE_LOSS_RTOL, BF16_LOOSE_COS = 2e-2, 0.999
+
+
+def _run(z1, z2, *, cls="SP", target=None, mask=None, gamma=1e6, mode="hard", correct_grad=False,
+         temperature=0.07, precision="fp32"):
+    a = torch.as_tensor(z1).cuda().requires_grad_(True)
+    b = torch.as_tensor(z2).cuda().requires_grad_(True)
+    if cls == "SupConLoss1":
+        crit = spcl_b200.SupConLoss1(temperature=temperature, precision=precision)
+    else:
+        crit = spcl_b200.SelfPacedSupConLoss(temperature=temperature, weight_update=mode, correct_grad=correct_grad,
+                                             precision=precision)
+        crit.set_gamma(gamma)
+    kw = {}
+    if mask is not None:
+        kw["mask"] = torch.as_tensor(mask).cuda()
+    elif target is not None:
+        kw["target"] = torch.as_tensor(target).cuda() if isinstance(target, np.ndarray) else target
+    loss = crit(a, b, **kw)
+    loss.backward()
+    ratio = crit.downgrade_ratio if cls != "SupConLoss1" else float("nan")
+    return dict(loss=loss.item(), ratio=ratio, dz1=a.grad.cpu().numpy(), dz2=b.grad.cpu().numpy(), crit=crit)
+
+
+def _grad_metrics(res, ref):
+    g = np.concatenate([res["dz1"], res["dz2"]]).astype(np.float64)
+    r = np.concatenate([np.asarray(ref["dz1"]), np.asarray(ref["dz2"])]).astype(np.float64)
+    rel = np.abs(g - r).max() / np.abs(r).max()
+    cos = (g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r))
+    return rel, cos
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 path vs the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CFG1.cases)
+def test_fp32_path_matches_reference_cfg1(name):
+    kw = parse_cfg1_case(name, CFG1)
+    res = _run(CFG1["z1"], CFG1["z2"], precision="fp32", **kw)
+    ref = CFG1.case(name)
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL), (res["loss"], ref["loss"])
+    if kw["cls"] != "SupConLoss1":
+        assert np.isclose(res["ratio"], ref["ratio"], rtol=1e-5, atol=1e-7)
+    rel, _ = _grad_metrics(res, ref)
+    assert rel < FP32_GRAD_REL, rel
+
+
+@pytest.mark.parametrize("name", CFG2.cases)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg2_matches_reference(name, precision):
+    z1, z2 = CFG2[f"{name}/z1"], CFG2[f"{name}/z2"]
+    res = _run(z1, z2, target=CFG2[f"{name}/labels"].tolist(), gamma=float(CFG2[f"{name}/gamma"]), mode="soft",
+               precision=precision)
+    ref = CFG2.case(name)
+    rel, cos = _grad_metrics(res, ref)
+    if precision == "fp32":
+        assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL)
+        assert rel < FP32_GRAD_REL
+    else:
+        assert np.isclose(res["loss"], ref["loss"], rtol=BF16_LOOSE_LOSS_RTOL)
+        assert cos > BF16_LOOSE_COS, cos
+
+
+@pytest.mark.parametrize("name", TINY.cases)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tiny_ragged_batch(name, precision):
+    labels = TINY["labels"].tolist()
+    kw = {"sp_soft_g3": dict(target=labels, gamma=3.0, mode="soft"),
+          "sp_hard_g3": dict(target=labels, gamma=3.0, mode="hard"),
+          "supcon1": dict(cls="SupConLoss1", target=labels),
+          "sp_simclr": dict(gamma=4.0, mode="soft")}[name]
+    res = _run(TINY["z1"], TINY["z2"], precision=precision, **kw)
+    ref = TINY.case(name)
+    if precision == "fp32":
+        assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL)
+        assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL
+    else:
+        assert np.isclose(res["loss"], ref["loss"], rtol=5e-2, atol=5e-3)
+        assert _grad_metrics(res, ref)[1] > 0.99
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [c for c in CFG1.cases if "trimask" not in c])
+def test_bf16_path_cfg1(name):
+    kw = parse_cfg1_case(name, CFG1)
+    res = _run(CFG1["z1"], CFG1["z2"], precision="bf16", **kw)
+    # (a) tight: oracle on the bf16-rounded operands
+    zb1 = torch.from_numpy(CFG1["z1"]).bfloat16().float().numpy()
+    zb2 = torch.from_numpy(CFG1["z2"]).bfloat16().float().numpy()
+    okw = {k: v for k, v in kw.items() if k != "cls"}
+    tight = supcon_closed_form(zb1, zb2, **okw)
+    ref = CFG1.case(name)
+    if kw["mode"] == "hard" and kw["gamma"] < 1e5:
+        # a pair whose loss sits within rounding of gamma may flip: allow two flips, state it
+        n_pos = tight["c"].sum()
+        assert abs(res["ratio"] - tight["ratio"]) <= 2.0 / n_pos + 1e-6
+        assert np.isclose(res["loss"], tight["loss"], rtol=2e-2)
+    else:
+        assert np.isclose(res["loss"], tight["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], tight["loss"])
+        if kw["cls"] != "SupConLoss1":
+            assert np.isclose(res["ratio"], tight["ratio"], rtol=1e-4, atol=1e-6)
+        rel, cos = _grad_metrics(res, tight)
+        assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (rel, cos)
+    # (b) loose: the reference on the raw fp32 inputs
+    assert np.isclose(res["loss"], ref["loss"], rtol=BF16_LOOSE_LOSS_RTOL)
+    assert _grad_metrics(res, ref)[1] > BF16_LOOSE_COS
+
+
+@pytest.mark.parametrize("n,d,kind", [(75, 96, "partition"), (192, 64, "patient"), (129, 200, "cycle"),
+                                      (640, 128, "composite"), (300, 256, "self")])
+@pytest.mark.parametrize("mode", ["none", "soft"])
+def test_bf16_path_shapes(n, d, kind, mode):
+    labels = acdc_meta_labels(n)[kind]
+    z1, z2 = make_views(labels, d, sigma=0.7, seed=n)
+    z1, z2 = z1.bfloat16().float(), z2.bfloat16().float()
+    cls = "SupConLoss1" if mode == "none" else "SP"
+    res = _run(z1, z2, cls=cls, target=labels.tolist(), gamma=6.0, mode=mode, correct_grad=(mode == "soft"),
+               precision="bf16")
+    ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=6.0, mode=mode,
+                             correct_grad=(mode == "soft"))
+    assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], ref["loss"])
+    rel, cos = _grad_metrics(res, ref)
+    assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (rel, cos)
+
+
+def test_bf16_and_fp32_paths_agree_n4096():
+    z1, z2, labels = make_workload("cfg3_dense_2x16384_d128_slice")
+    z1, z2, labels = z1[:2048].bfloat16().float(), z2[:2048].bfloat16().float(), labels[:2048] // 8
+    a = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="fp32")
+    b = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="bf16")
+    assert np.isclose(a["loss"], b["loss"], rtol=BF16_TIGHT_LOSS_RTOL)
+    assert np.isclose(a["ratio"], b["ratio"], rtol=1e-4)
+    rel, cos = _grad_metrics(b, a)
+    assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE full size (cfg3: N = 32768, d = 128): fp64 torch reference on the GPU + size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_torch_ref_matches_oracle():
+    kw = dict(gamma=5.0, mode="soft", correct_grad=True)
+    lab = torch.from_numpy(CFG1["labels_patient"])
+    ref = supcon_closed_form(CFG1["z1"], CFG1["z2"], target=lab.tolist(), **kw)
+    out = supcon_ref64(torch.from_numpy(CFG1["z1"]).cuda(), torch.from_numpy(CFG1["z2"]).cuda(), lab.cuda(), **kw)
+    assert np.isclose(out["loss"], ref["loss"], rtol=1e-10)
+    np.testing.assert_allclose(out["dz1"].cpu().numpy(), ref["dz1"], rtol=1e-8, atol=1e-14)
+
+
+@pytest.mark.parametrize("workload,mode,gamma", [
+    ("cfg3_dense_2x16384_d128_simclr", "soft", 8.0),
+    ("cfg3_dense_2x16384_d128_slice", "soft", 10.0),
+    ("cfg3_dense_2x16384_d128_slice", "none", 1e6),
+])
+def test_cfg3_full_size_against_fp64(workload, mode, gamma):
+    z1, z2, labels = make_workload(workload)
+    z1, z2 = z1.bfloat16().float().cuda(), z2.bfloat16().float().cuda()
+    lab = labels.int().cuda()
+    cls = "SupConLoss1" if mode == "none" else "SP"
+    res = _run(z1, z2, cls=cls, target=lab, gamma=gamma, mode=mode, precision="bf16")
+    ref = supcon_ref64(z1, z2, lab, gamma=gamma, mode=mode)
+    assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], ref["loss"])
+    if mode != "none":
+        assert np.isclose(res["ratio"], ref["ratio"], rtol=2e-4)
+    logD = res["crit"]._diag.row_stats[: 2 * z1.shape[0], 0].double()
+    assert (logD - ref["logD"]).abs().max().item() < 2e-4
+    ref_np = dict(dz1=ref["dz1"].cpu().numpy(), dz2=ref["dz2"].cpu().numpy())
+    rel, cos = _grad_metrics(res, ref_np)
+    assert rel < 3e-2 and cos > BF16_TIGHT_COS, (rel, cos)
+
+
+def test_cfg3_properties():
+    z1, z2, labels = make_workload("cfg3_dense_2x16384_d128_simclr")
+    n, d = z1.shape
+    # (1) gamma -> inf (hard) == SupConLoss1   (reference __main__ identity, contrast_loss2.py:330-346)
+    a = _run(z1, z2, target=labels.int().numpy(), gamma=1e6, mode="hard", precision="bf16")
+    b = _run(z1, z2, cls="SupConLoss1", target=labels.int().numpy(), precision="bf16")
+    assert np.isclose(a["loss"], b["loss"], rtol=1e-5) and a["ratio"] == 1.0
+    assert _grad_metrics(a, b)[0] < 1e-3
+    # (2) target=range(n) == no target (SimCLR)
+    c = _run(z1, z2, gamma=1e6, mode="hard", precision="bf16")
+    assert np.isclose(a["loss"], c["loss"], rtol=1e-6)
+    # (3) rotation invariance of f(Z Z^T)  =>  Z^T dZ is symmetric
+    Z = np.concatenate([z1.numpy(), z2.numpy()]).astype(np.float64)
+    G = np.concatenate([a["dz1"], a["dz2"]]).astype(np.float64)
+    M = Z.T @ G
+    assert np.abs(M - M.T).max() <= 2e-2 * np.abs(M).max()
+    # (4) anchor permutation equivariance
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5))
+    p = _run(z1[perm], z2[perm], target=labels[perm].int().numpy(), gamma=1e6, mode="hard", precision="bf16")
+    assert np.isclose(a["loss"], p["loss"], rtol=1e-5)
+    assert np.abs(p["dz1"] - a["dz1"][perm.numpy()]).max() <= 2e-2 * np.abs(a["dz1"]).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and error behaviour
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_single_pair_batch(precision):
+    z = F.normalize(torch.randn(1, 32, generator=torch.Generator().manual_seed(1)), dim=1)
+    res = _run(z, z.clone(), precision=precision, gamma=3.0, mode="soft")
+    assert abs(res["loss"]) < 1e-5 and np.isfinite(res["dz1"]).all()
+
+
+def test_zero_positive_row_raises_runtime_error():
+    n = 8
+    z1, z2 = make_views(torch.arange(n) % 2, 32, seed=3)
+    tri = torch.ones(n, n)
+    tri[0, :] = 0.0                      # anchor 0 (and n) has no positive at all -> 0/0 (:196, :203)
+    crit = spcl_b200.SupConLoss1()
+    with pytest.raises(RuntimeError):
+        crit(z1.cuda(), z2.cuda(), mask=tri.cuda())
+
+
+def test_trimask_needs_fp32_path():
+    z1, z2 = make_views(torch.arange(8) % 2, 32, seed=3)
+    crit = spcl_b200.SupConLoss1(precision="bf16")
+    with pytest.raises(nat.SpclError):
+        crit(z1.cuda(), z2.cuda(), mask=torch.ones(8, 8).cuda())
+
+
+def test_unnormalised_input_asserts():
+    crit = spcl_b200.SupConLoss1()
+    with pytest.raises(AssertionError):
+        crit(torch.randn(8, 16).cuda(), torch.randn(8, 16).cuda())
+
+
+def test_non_contiguous_and_half_inputs():
+    labels = acdc_meta_labels(64)["partition"]
+    z1, z2 = make_views(labels, 128, seed=0)
+    wide1 = torch.zeros(64, 256); wide1[:, :128] = z1
+    wide2 = torch.zeros(64, 256); wide2[:, :128] = z2
+    a = _run(z1, z2, target=labels.tolist(), gamma=5.0, mode="soft", precision="fp32")
+    crit = spcl_b200.SelfPacedSupConLoss(weight_update="soft"); crit.set_gamma(5.0)
+    loss = crit(wide1.cuda()[:, :128], wide2.cuda()[:, :128], target=labels.tolist())
+    assert np.isclose(loss.item(), a["loss"], rtol=1e-6)
+    crit16 = spcl_b200.SelfPacedSupConLoss(weight_update="soft", validate=False); crit16.set_gamma(5.0)
+    h1 = z1.cuda().half().requires_grad_(True)
+    loss16 = crit16(h1, z2.cuda().half(), target=labels.tolist())
+    loss16.backward()
+    assert np.isclose(loss16.item(), a["loss"], rtol=2e-2) and h1.grad.dtype == torch.float16
+
+
+def test_diagnostics_match_reference_semantics():
+    labels = CFG1["labels_partition"].tolist()
+    res = _run(CFG1["z1"], CFG1["z2"], target=labels, gamma=5.0, mode="soft", precision="fp32")
+    crit = res["crit"]
+    ref = dense_supcon(torch.from_numpy(CFG1["z1"]), torch.from_numpy(CFG1["z2"]), target=labels, gamma=5.0,
+                       mode="soft")
+    assert torch.equal(crit.pos_mask.cpu(), ref.pos_mask)            # bit-exact masks
+    assert torch.equal(crit.neg_mask.cpu(), ref.neg_mask)
+    assert torch.allclose(crit.sim_logits.cpu(), ref.sim_logits, atol=1e-4)
+    assert torch.allclose(crit.sim_exp.cpu(), ref.sim_exp, atol=1e-5)
+    assert torch.allclose(crit.sp_mask.cpu(), ref.sp_mask, atol=1e-4)
+    assert isinstance(crit.downgrade_ratio, float) and crit.age_param == 5.0
+
+
+def test_grad_scales_with_upstream_gradient():
+    labels = acdc_meta_labels(64)["partition"]
+    z1, z2 = make_views(labels, 128, seed=0)
+    for precision in ("fp32", "bf16"):
+        crit = spcl_b200.SupConLoss1(precision=precision)
+        a = z1.cuda().requires_grad_(True)
+        (crit(a, z2.cuda(), target=labels.tolist()) * 2.5).backward()
+        g1 = a.grad.clone(); a.grad = None
+        crit(a, z2.cuda(), target=labels.tolist()).backward()
+        assert torch.allclose(g1, 2.5 * a.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_opcheck_registration():
+    labels = acdc_meta_labels(64)["partition"].int().cuda()
+    z1, z2 = make_views(labels.cpu(), 128, seed=0)
+    args = (z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True), labels, None, 0.07, 5.0, 2, False, False)
+    torch.library.opcheck(spcl_b200.ops.supcon_fwd, args, test_utils=("test_schema", "test_faketensor"))
+
+
+# ------------------------------------------------------------------------------------------------
+# projector tail
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 256), (4096, 128), (32, 128, 32, 32), (7, 33), (3, 5, 7), (2, 256, 10, 10)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_l2norm_matches_torch(shape, dtype):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(*shape, generator=g).to(dtype).cuda().requires_grad_(True)
+    y = spcl_b200.Normalize(dim=1)(x)
+    go = torch.randn(*shape, generator=g).to(dtype).cuda()
+    y.backward(go)
+    x2 = x.detach().float().requires_grad_(True)
+    y2 = F.normalize(x2, p=2, dim=1)
+    y2.backward(go.float())
+    tol = 1e-6 if dtype == torch.float32 else 1.6e-2
+    assert (y.float() - y2).abs().max().item() <= tol
+    assert (x.grad.float() - x2.grad).abs().max().item() <= tol * max(1.0, x2.grad.abs().max().item())
+
+
+def test_l2norm_zero_row_uses_eps_like_torch():
+    x = torch.zeros(4, 16).cuda(); x[1] = 1.0
+    y = spcl_b200.normalize(x)
+    assert torch.equal(y[0], torch.zeros(16).cuda()) and torch.allclose(y, F.normalize(x))

@@ -1,0 +1,145 @@
+"""Host-side logic and the C-ABI surface; no GPU needed."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import spcl_b200
+from spcl_b200 import _native as nat
+from spcl_b200 import ops
+from spcl_b200.losses import _pick_tc
+from oracle.closed_form import codes_from_target
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def _same_classes(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.array_equal(a[:, None] == a[None, :], b[:, None] == b[None, :])
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "spcl.h").read_text()
+    declared = set(re.findall(r"\b(spcl_[a-z0-9_]+)\s*\(", header))
+    declared.discard("spcl_error_string() ")
+    assert declared == set(nat.ALL_SYMBOLS), declared ^ set(nat.ALL_SYMBOLS)
+    handle = nat.lib()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.spcl_version() >= 100
+    assert handle.spcl_error_string(0) == b"ok"
+
+
+def test_abi_validates_arguments_without_touching_the_gpu():
+    h = nat.lib()
+    null = ctypes.c_void_p(0)
+    rc = h.spcl_supcon_fwd_f32(null, 128, 64, 64, null, null, 64, 0, 128, 14.0, 1.0, 0, null, null, null)
+    assert rc == -1
+    rc = h.spcl_supcon_finalize(null, 0, 0, null, null)
+    assert rc == -1
+    fake = ctypes.c_void_p(4096)
+    # d > SPCL_MAX_D is rejected before any launch
+    rc = h.spcl_supcon_fwd_f32(fake, 128, 512, 512, fake, null, 64, 0, 128, 14.0, 1.0, 0, fake, fake, null)
+    assert rc == -2
+    # row_begin must be tile aligned on the tensor-core path
+    rc = h.spcl_supcon_fwd_bf16(fake, 256, 256, 128, fake, fake, 64, 256, 14.0, 1.0, 0, fake, fake, fake, null)
+    assert rc == -2
+    assert b"invalid" in h.spcl_error_string(-1)
+
+
+@pytest.mark.parametrize("target", [
+    [0, 1, 2, 0, 1, 2], [5, 5, 5, 5, 5, 5], [2 ** 24, 2 ** 24 + 1, 7, 7, 2 ** 24 + 2, 0],
+    [0.5, 0.25, 0.5, 1.0, 1.0, 0.25], [-3, 3, -3, 3, 0, 0],
+])
+def test_label_codes_lists_match_reference_semantics(target):
+    codes = ops.label_codes(target, len(target), "cpu").numpy()
+    assert codes.dtype == np.int32
+    assert _same_classes(codes, codes_from_target(target))
+    # and against the reference's literal construction (contrast_loss3.py:135-136)
+    t = torch.Tensor(target)
+    assert np.array_equal((t[:, None] == t[None, :]).numpy(), codes[:, None] == codes[None, :])
+
+
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.uint8, torch.float32])
+def test_label_codes_tensors(dtype):
+    t = torch.tensor([3, 1, 3, 0, 1, 200], dtype=dtype)
+    codes = ops.label_codes(t, 6, "cpu").numpy()
+    assert _same_classes(codes, t.numpy())
+    big = torch.tensor([2 ** 40, 2 ** 40 + 1, 2 ** 40], dtype=torch.int64)
+    assert _same_classes(ops.label_codes(big, 3, "cpu").numpy(), big.numpy())
+
+
+def test_label_codes_shape_errors():
+    with pytest.raises(AssertionError):
+        ops.label_codes([0, 1, 2], 4, "cpu")
+    with pytest.raises(TypeError):
+        ops.label_codes("abc", 3, "cpu")
+
+
+def test_tri_codes():
+    m = torch.tensor([[1.0, 0.0, 0.5], [2.0, 1.0, 0.0], [0.0, -1.0, 1.0]])
+    out = ops.tri_codes(m, 3, "cpu")
+    assert out.tolist() == [[1, 0, 2], [2, 1, 0], [0, 2, 1]]
+
+
+def test_precision_policy():
+    assert _pick_tc("bf16", 128, False) and not _pick_tc("fp32", 10 ** 6, False)
+    assert not _pick_tc("auto", 512, False) and _pick_tc("auto", 1024, False)
+    assert not _pick_tc("auto", 10 ** 5, True)        # tri-state mask -> fp32 path
+    with pytest.raises(ValueError):
+        _pick_tc("fp8", 128, False)
+
+
+def test_module_surface_matches_reference():
+    sp = spcl_b200.SelfPacedSupConLoss(temperature=0.1, weight_update="soft", correct_grad=True)
+    assert sp.age_param == 1e6                       # contrast_loss3.py:122
+    sp.set_gamma(3)
+    assert sp.age_param == 3.0 and isinstance(sp.age_param, float)
+    assert repr(sp) == "SelfPacedSupConLoss with T: 0.1, method: soft gamma: 3.0"
+    s1 = spcl_b200.SupConLoss1()
+    assert s1._t == 0.07
+    with pytest.raises(NotImplementedError):
+        spcl_b200.SupConLoss1(exclude_other_pos=True)
+    with pytest.raises(AttributeError):
+        _ = sp.downgrade_ratio                       # only after a forward call
+
+
+def test_no_cpu_fallback():
+    z = torch.nn.functional.normalize(torch.randn(8, 16), dim=1)
+    crit = spcl_b200.SupConLoss1()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        crit(z, z.clone(), target=[0, 1] * 4)
+    with pytest.raises(AssertionError):             # the reference's shape assert (:155)
+        crit(z, z[:4], target=[0, 1] * 4)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(nat.SpclError, match="no CPU/PyTorch fallback"):
+        nat.lib()
+
+
+def test_pscheduler_follows_reference_formula():
+    s = spcl_b200.PScheduler(max_epoch=80, begin_value=2.0, end_value=60.0, p=0.5)
+    vals = []
+    for _ in range(5):
+        vals.append(s.value)
+        s.step()
+    expect = [2.0 + 58.0 * (e / 80) ** 0.5 for e in range(5)]     # semi_seg/hooks/infonce.py:50-53
+    assert np.allclose(vals, expect)
+    st = s.state_dict()
+    s2 = spcl_b200.PScheduler(max_epoch=80, begin_value=2.0, end_value=60.0, p=0.5)
+    s2.load_state_dict(st)
+    assert s2.value == s.value
+
+
+def test_workload_shapes():
+    from spcl_b200.workloads import WORKLOADS, make_workload
+    z1, z2, lab = make_workload("cfg1_cpu_2x64_d128")
+    assert z1.shape == (64, 128) and lab.shape == (64,)
+    assert torch.allclose(z1.norm(dim=1), torch.ones(64), atol=1e-5)
+    assert set(WORKLOADS) >= {"cfg2_encoder_2x256_d256", "cfg3_dense_2x16384_d128_simclr"}
