@@ -19,9 +19,9 @@
  *     anything else = ignored (reference: mask == 1 / mask == 0, :130-131).
  *   - mode: SPCL_MODE_NONE = SupConLoss1 (W == 1), HARD / SOFT = SelfPacedSupConLoss._self_paced_mask :207-214.
  *   - row sharding: a call owns anchor rows [row_begin, row_end) against all N columns.
- *   - row_stats: float[N][4] = { logD_i, 1/c_i, A_i, u_i } with logD_i the natural-log row
- *     logsumexp over valid columns, c_i the positive count, A_i = sum_j W_ij P_ij / c_i and
- *     u_i = A_i * exp(1/tau - logD_i).
+ *   - row_stats: four planes of `stride` floats each (stride = n_pad on the tensor-core path):
+ *     plane 0 logD_i (natural-log row logsumexp over valid columns), plane 1 1/c_i (c_i = positive
+ *     count), plane 2 A_i = sum_j W_ij P_ij / c_i, plane 3 u_i = A_i * exp(1/tau - logD_i).
  *   - partials: float[3] = { sum_i (1/c_i) sum_j W P LLH , sum W P , sum P } accumulated with
  *     atomicAdd (zero them first; all-reduce them across ranks when rows are sharded).
  *   - scalars: float[4] = { loss, downgrade_ratio, grad scale, scale / N }.
@@ -101,10 +101,11 @@ int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t
  * z: float [n_total][ldz].  Exactly one of labels / tri may be non-NULL (tri needs n_half = N/2). */
 int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
                         const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end, float inv_tau,
-                        float gamma, int mode, float* row_stats, float* partials, spcl_stream_t stream);
+                        float gamma, int mode, float* row_stats, int64_t stats_stride, float* partials,
+                        spcl_stream_t stream);
 int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
-                        const uint8_t* tri, int64_t n_half, const float* row_stats, const float* scalars,
-                        const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
+                        const uint8_t* tri, int64_t n_half, const float* row_stats, int64_t stats_stride,
+                        const float* scalars, const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
                         int mode, float* dz, int64_t lddz, spcl_stream_t stream);
 
 /* ---- scalar epilogue (after the optional all-reduce of partials) ------------------------------

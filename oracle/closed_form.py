@@ -99,13 +99,15 @@ class _Masks:
 def supcon_closed_form(z1, z2, *, target=None, mask=None, temperature: float = 0.07,
                        gamma: float = 1e6, mode: str = "hard", correct_grad: bool = False,
                        block: int = 512, grad_out: float = 1.0, want_grad: bool = True,
-                       row_range=None) -> dict:
+                       row_range=None, anchor_labels=None) -> dict:
     """Loss, ratio and gradient in fp64.
 
     ``mode``: "none" (SupConLoss1), "hard", anything else = soft.
     ``row_range``: optional (r0, r1) -- only these anchor rows contribute to the
     *partial* sums returned under ``partial`` (used by the row-sharding tests);
     ``loss``/``ratio`` are always the full-problem values.
+    ``anchor_labels``: optional integer label per ANCHOR (length N = 2n) instead of per sample; used by
+    the row-sharding tests, where the global anchor order is (rank, view, sample) rather than (view, sample).
     Precedence mask > target > identity follows contrast_loss3.py:128-143.
     """
     z1 = np.asarray(z1, dtype=np.float64)
@@ -116,7 +118,11 @@ def supcon_closed_form(z1, z2, *, target=None, mask=None, temperature: float = 0
     Z = np.concatenate([z1, z2], axis=0)
     inv_tau = 1.0 / float(temperature)
 
-    if mask is not None:
+    if anchor_labels is not None:
+        masks = _Masks(n, codes=None)
+        masks.codes = codes_from_target(np.asarray(anchor_labels))
+        assert masks.codes.shape[0] == N
+    elif mask is not None:
         tri = np.asarray(mask)
         assert tri.shape == (n, n)
         masks = _Masks(n, tri=tri)

@@ -91,7 +91,8 @@ __device__ __forceinline__ float row_sum16(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(NT) fwd_kernel(Args p, float4* __restrict__ row_stats, float* __restrict__ partials) {
+__global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row_stats, int64_t sld,
+                                                 float* __restrict__ partials) {
   __shared__ Smem sm;
   __shared__ float red[3][BM];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -183,7 +184,10 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float4* __restrict__ ro
         const float invc = 1.f / cnt[a];          // c == 0 -> inf -> NaN loss, like the reference's 0/0
         const float A = wp[a] * invc;
         const float u = A * expf(shift - logD[a]);
-        row_stats[gi[a]] = make_float4(logD[a], invc, A, u);
+        row_stats[gi[a]] = logD[a];
+        row_stats[sld + gi[a]] = invc;
+        row_stats[2 * sld + gi[a]] = A;
+        row_stats[3 * sld + gi[a]] = u;
         l = wl[a] * invc;
         w = wp[a];
         c = cnt[a];
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float4* __restrict__ ro
 }
 
 template <int DV>
-__global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float4* __restrict__ row_stats,
+__global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float* __restrict__ row_stats, int64_t sld,
                                                  const float* __restrict__ scalars,
                                                  const float* __restrict__ grad_out, float* __restrict__ dz,
                                                  int64_t lddz) {
@@ -221,7 +225,8 @@ __global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float4* __restric
     gi[a] = i0 + ty * 4 + a;
     const bool ok = gi[a] < p.N;
     li[a] = (p.labels != nullptr && ok) ? p.labels[gi[a]] : 0;
-    si[a] = ok ? row_stats[gi[a]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    si[a] = ok ? make_float4(row_stats[gi[a]], row_stats[sld + gi[a]], 0.f, row_stats[3 * sld + gi[a]])
+               : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   float dzacc[4][DV];
@@ -239,7 +244,8 @@ __global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float4* __restric
       const int64_t gj = j0 + cj;
       const bool col_ok = gj < p.N;
       const int lj = (p.labels != nullptr && col_ok) ? p.labels[gj] : 0;
-      const float4 sj = col_ok ? row_stats[gj] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 sj = col_ok ? make_float4(row_stats[gj], row_stats[sld + gj], 0.f, row_stats[3 * sld + gj])
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         float t = 0.f;
@@ -321,35 +327,35 @@ using namespace spcl;
 
 extern "C" int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
                                    const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end,
-                                   float inv_tau, float gamma, int mode, float* row_stats, float* partials,
-                                   spcl_stream_t stream) {
+                                   float inv_tau, float gamma, int mode, float* row_stats, int64_t stats_stride,
+                                   float* partials, spcl_stream_t stream) {
   int rc = simt::check_common(z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
-  if (row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
+  if (row_stats == nullptr || partials == nullptr || stats_stride < n_total) return SPCL_ERR_INVALID_ARG;
   simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
   const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
   simt::fwd_kernel<<<grid, simt::NT, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, reinterpret_cast<float4*>(row_stats), partials);
+      a, row_stats, stats_stride, partials);
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_f32");
   return SPCL_OK;
 }
 
 extern "C" int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
                                    const uint8_t* tri, int64_t n_half, const float* row_stats,
-                                   const float* scalars, const float* grad_out, int64_t row_begin,
+                                   int64_t stats_stride, const float* scalars, const float* grad_out, int64_t row_begin,
                                    int64_t row_end, float inv_tau, float gamma, int mode, float* dz, int64_t lddz,
                                    spcl_stream_t stream) {
   int rc = simt::check_common(z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
-  if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d)
+  if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d ||
+      stats_stride < n_total)
     return SPCL_ERR_INVALID_ARG;
   simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
   const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const float4* st = reinterpret_cast<const float4*>(row_stats);
-  if (d <= 64) simt::bwd_kernel<4><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
-  else if (d <= 128) simt::bwd_kernel<8><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
-  else simt::bwd_kernel<16><<<grid, simt::NT, 0, s>>>(a, st, scalars, grad_out, dz, lddz);
+  if (d <= 64) simt::bwd_kernel<4><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else if (d <= 128) simt::bwd_kernel<8><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else simt::bwd_kernel<16><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_f32");
   return SPCL_OK;
 }

@@ -71,11 +71,11 @@ class NativeBackend:
         sig = torch.empty(N // nat.TILE, 4, dtype=torch.int32, device=dev)
         nat.call("spcl_label_block_sig", _ptr(labels_all), N, N, _ptr(sig), st)
         acc = torch.empty(N, 4, dtype=torch.float32, device=dev)
-        row_stats = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        row_stats = torch.zeros(4, N, dtype=torch.float32, device=dev)
         partials = torch.zeros(3, dtype=torch.float32, device=dev)
         nat.call("spcl_supcon_fwd_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig), plan.row_begin,
                  plan.row_end, inv_tau, gamma, mode, _ptr(acc), _ptr(row_stats), _ptr(partials), st)
-        return row_stats[plan.row_begin:plan.row_end].contiguous(), partials, sig
+        return row_stats[:, plan.row_begin:plan.row_end].contiguous(), partials, sig
 
     def finalize(self, partials, N, correct_grad):
         scalars = torch.empty(4, dtype=torch.float32, device=partials.device)
@@ -112,7 +112,8 @@ class _ShardedSupCon(torch.autograd.Function):
         stats_loc, partials, sig = backend.forward_rows(z_all, labels_all, plan, inv_tau, float(gamma), int(mode))
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)    # 3 floats
         scalars = backend.finalize(partials, plan.N, bool(correct_grad))
-        stats_all = _gather_rows(stats_loc, world, group)               # 16 B per anchor
+        # 16 B per anchor; ranks contribute [4, rows_loc] plane slices -> [4, N] planes
+        stats_all = _gather_rows(stats_loc, world, group).view(world, 4, -1).permute(1, 0, 2).reshape(4, -1).contiguous()
         ctx.save_for_backward(z_all, labels_all, sig, stats_all, scalars)
         ctx.meta = (plan, inv_tau, float(gamma), int(mode), d, backend)
         ctx.mark_non_differentiable(scalars)

@@ -92,7 +92,7 @@ class _Diagnostics:
         if name == "sp_mask":
             N = c["pos"].shape[0]
             z = torch.cat([self.z1, self.z2]).float()
-            llh = (z @ z.t()) / self.t - self.row_stats[:N, 0:1]
+            llh = (z @ z.t()) / self.t - self.row_stats[0, :N, None]
             l = -llh
             if self.mode == nat.MODE_NONE:
                 w = torch.ones_like(l)

@@ -91,7 +91,7 @@ def tri_codes(mask: Tensor, n: int, device) -> Tensor:
 def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[Tensor], temperature: float,
                gamma: float, mode: int, correct_grad: bool, use_tc: bool
                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> (scalars[4] = loss, ratio, scale, scale/N ; row_stats[n_pad, 4] ; packed operands ;
+    """-> (scalars[4] = loss, ratio, scale, scale/N ; row_stats[4, n_pad] ; packed operands ;
     labels_full int32[n_pad] ; block signatures int32[n_pad/128, 4])."""
     _require_cuda(z1, z2, labels, tri)
     if z1.shape != z2.shape or z1.dim() != 2:
@@ -112,7 +112,7 @@ def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[T
     n_pad = pad_to(N, nat.TILE)
     st = _stream(z1)
     inv_tau = 1.0 / float(temperature)
-    row_stats = torch.zeros(n_pad, 4, dtype=torch.float32, device=dev)
+    row_stats = torch.zeros(4, n_pad, dtype=torch.float32, device=dev)
     partials = torch.zeros(3, dtype=torch.float32, device=dev)
     scalars = torch.empty(4, dtype=torch.float32, device=dev)
 
@@ -140,7 +140,7 @@ def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[T
         sig = torch.empty(0, 4, dtype=torch.int32, device=dev)
         nat.call("spcl_supcon_fwd_f32", _ptr(zpack), N, d, zpack.stride(0),
                  _ptr(labels_full) if labels is not None else None, _ptr(tri), n, 0, N, inv_tau, float(gamma),
-                 int(mode), _ptr(row_stats), _ptr(partials), st)
+                 int(mode), _ptr(row_stats), n_pad, _ptr(partials), st)
     nat.call("spcl_supcon_finalize", _ptr(partials), N, int(bool(correct_grad)), _ptr(scalars), st)
     return scalars, row_stats, zpack, labels_full, sig
 
@@ -150,7 +150,7 @@ def _(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc):
     n, d = z1.shape
     n_pad = pad_to(2 * n, nat.TILE)
     scalars = z1.new_empty(4)
-    row_stats = z1.new_empty(n_pad, 4)
+    row_stats = z1.new_empty(4, n_pad)
     if use_tc:
         zpack = z1.new_empty(n_pad, pad_to(d, 64), dtype=torch.bfloat16)
         sig = z1.new_empty(n_pad // nat.TILE, 4, dtype=torch.int32)
@@ -180,8 +180,8 @@ def supcon_bwd(grad_loss: Tensor, zpack: Tensor, labels_full: Tensor, sig: Tenso
                  dz.stride(0), st)
     else:
         nat.call("spcl_supcon_bwd_f32", _ptr(zpack), N, d, zpack.stride(0),
-                 _ptr(labels_full) if tri is None else None, _ptr(tri), n, _ptr(row_stats), _ptr(scalars),
-                 _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz), dz.stride(0), st)
+                 _ptr(labels_full) if tri is None else None, _ptr(tri), n, _ptr(row_stats),
+                 row_stats.stride(0), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz), dz.stride(0), st)
     return dz
 
 

@@ -30,14 +30,14 @@ BF16_LOOSE_LOSS_RTOL, BF16_LOOSE_COS = 2e-2, 0.999
 
 
 def _run(z1, z2, *, cls="SP", target=None, mask=None, gamma=1e6, mode="hard", correct_grad=False,
-         temperature=0.07, precision="fp32"):
+         temperature=0.07, precision="fp32", validate=True):
     a = torch.as_tensor(z1).cuda().requires_grad_(True)
     b = torch.as_tensor(z2).cuda().requires_grad_(True)
     if cls == "SupConLoss1":
-        crit = spcl_b200.SupConLoss1(temperature=temperature, precision=precision)
+        crit = spcl_b200.SupConLoss1(temperature=temperature, precision=precision, validate=validate)
     else:
         crit = spcl_b200.SelfPacedSupConLoss(temperature=temperature, weight_update=mode, correct_grad=correct_grad,
-                                             precision=precision)
+                                             precision=precision, validate=validate)
         crit.set_gamma(gamma)
     kw = {}
     if mask is not None:
@@ -53,6 +53,8 @@ def _run(z1, z2, *, cls="SP", target=None, mask=None, gamma=1e6, mode="hard", co
 def _grad_metrics(res, ref):
     g = np.concatenate([res["dz1"], res["dz2"]]).astype(np.float64)
     r = np.concatenate([np.asarray(ref["dz1"]), np.asarray(ref["dz2"])]).astype(np.float64)
+    if np.abs(r).max() == 0.0:           # e.g. hard weighting with every positive above gamma: zero gradient
+        return (0.0, 1.0) if np.abs(g).max() < 1e-12 else (np.inf, 0.0)
     rel = np.abs(g - r).max() / np.abs(r).max()
     cos = (g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r))
     return rel, cos
@@ -145,7 +147,7 @@ def test_bf16_path_shapes(n, d, kind, mode):
     z1, z2 = z1.bfloat16().float(), z2.bfloat16().float()
     cls = "SupConLoss1" if mode == "none" else "SP"
     res = _run(z1, z2, cls=cls, target=labels.tolist(), gamma=6.0, mode=mode, correct_grad=(mode == "soft"),
-               precision="bf16")
+               precision="bf16", validate=False)
     ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=6.0, mode=mode,
                              correct_grad=(mode == "soft"))
     assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], ref["loss"])
@@ -156,8 +158,8 @@ def test_bf16_path_shapes(n, d, kind, mode):
 def test_bf16_and_fp32_paths_agree_n4096():
     z1, z2, labels = make_workload("cfg3_dense_2x16384_d128_slice")
     z1, z2, labels = z1[:2048].bfloat16().float(), z2[:2048].bfloat16().float(), labels[:2048] // 8
-    a = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="fp32")
-    b = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="bf16")
+    a = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="fp32", validate=False)
+    b = _run(z1, z2, target=labels.int().numpy(), gamma=8.0, mode="soft", precision="bf16", validate=False)
     assert np.isclose(a["loss"], b["loss"], rtol=BF16_TIGHT_LOSS_RTOL)
     assert np.isclose(a["ratio"], b["ratio"], rtol=1e-4)
     rel, cos = _grad_metrics(b, a)
@@ -186,12 +188,12 @@ def test_cfg3_full_size_against_fp64(workload, mode, gamma):
     z1, z2 = z1.bfloat16().float().cuda(), z2.bfloat16().float().cuda()
     lab = labels.int().cuda()
     cls = "SupConLoss1" if mode == "none" else "SP"
-    res = _run(z1, z2, cls=cls, target=lab, gamma=gamma, mode=mode, precision="bf16")
+    res = _run(z1, z2, cls=cls, target=lab, gamma=gamma, mode=mode, precision="bf16", validate=False)
     ref = supcon_ref64(z1, z2, lab, gamma=gamma, mode=mode)
     assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], ref["loss"])
     if mode != "none":
         assert np.isclose(res["ratio"], ref["ratio"], rtol=2e-4)
-    logD = res["crit"]._diag.row_stats[: 2 * z1.shape[0], 0].double()
+    logD = res["crit"]._diag.row_stats[0, : 2 * z1.shape[0]].double()
     assert (logD - ref["logD"]).abs().max().item() < 2e-4
     ref_np = dict(dz1=ref["dz1"].cpu().numpy(), dz2=ref["dz2"].cpu().numpy())
     rel, cos = _grad_metrics(res, ref_np)

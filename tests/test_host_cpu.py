@@ -36,13 +36,13 @@ def test_library_exports_every_declared_symbol():
 def test_abi_validates_arguments_without_touching_the_gpu():
     h = nat.lib()
     null = ctypes.c_void_p(0)
-    rc = h.spcl_supcon_fwd_f32(null, 128, 64, 64, null, null, 64, 0, 128, 14.0, 1.0, 0, null, null, null)
+    rc = h.spcl_supcon_fwd_f32(null, 128, 64, 64, null, null, 64, 0, 128, 14.0, 1.0, 0, null, 128, null, null)
     assert rc == -1
     rc = h.spcl_supcon_finalize(null, 0, 0, null, null)
     assert rc == -1
     fake = ctypes.c_void_p(4096)
     # d > SPCL_MAX_D is rejected before any launch
-    rc = h.spcl_supcon_fwd_f32(fake, 128, 512, 512, fake, null, 64, 0, 128, 14.0, 1.0, 0, fake, fake, null)
+    rc = h.spcl_supcon_fwd_f32(fake, 128, 512, 512, fake, null, 64, 0, 128, 14.0, 1.0, 0, fake, 128, fake, null)
     assert rc == -2
     # row_begin must be tile aligned on the tensor-core path
     rc = h.spcl_supcon_fwd_bf16(fake, 256, 256, 128, fake, fake, 64, 256, 14.0, 1.0, 0, fake, fake, fake, null)

@@ -51,7 +51,7 @@ def stage_tc_fwd(n=256, d=128, kind="partition"):
     for mode, name in ((0, "none"), (1, "hard"), (2, "soft")):
         loss, sc, aux = sp.supcon_loss(z1.cuda(), z2.cuda(), target=labels.tolist(), gamma=5.0, mode=mode, precision="bf16")
         ref = supcon_closed_form(zb1.numpy(), zb2.numpy(), target=labels.tolist(), gamma=5.0, mode=name, want_grad=False)
-        st = aux["row_stats"][:2 * n].cpu().numpy()
+        st = aux["row_stats"][:, :2 * n].cpu().numpy().T
         print(f"tc fwd n={n} d={d} {kind} {name}: loss {loss.item():.6f} ref(bf16 in) {ref['loss']:.6f} ratio {sc[1].item():.5f}/{ref['ratio']:.5f} "
               f"logD err {np.abs(st[:,0]-ref['logD']).max():.2e} c err {np.abs(1/st[:,1]-ref['c']).max():.2e}")
 
