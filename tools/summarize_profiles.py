@@ -1,0 +1,62 @@
+"""Turn the ncu artefacts of one GPU session (gpurun_out/<tag>_*) into the tracked summaries under profiles/."""
+import collections
+import csv
+import json
+import pathlib
+import subprocess
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+OUT = ROOT / "profiles"
+METRICS = [
+    "gpu__time_duration.sum", "smsp__cycles_elapsed.avg.per_second", "sm__cycles_active.avg",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_read.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
+]
+
+
+def launches(tag):
+    path = ROOT / "gpurun_out" / f"{tag}_launches.csv"
+    lines = [l for l in path.read_text().splitlines(True) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
+    total = sum(sum(v) for v in agg.values())
+    out = [f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 3)",
+           f"# per-launch times are cold-cache and serialised: compare SHARES.  total {total/1e3:.1f} us",
+           f"{'launches':>8} {'avg_us':>10} {'share_%':>8}  kernel"]
+    for k, v in agg.items():
+        out.append(f"{len(v):8d} {sum(v)/len(v)/1e3:10.2f} {100*sum(v)/total:8.2f}  {k[:110]}")
+    (OUT / f"{tag}_launches.txt").write_text("\n".join(out) + "\n")
+
+
+def full(tag, which):
+    rep = ROOT / "gpurun_out" / f"{tag}_prof_{which}.ncu-rep"
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    out = [f"# ncu --set full --clock-control none --import-source on -k regex:{which}_kernel  ({rep.name})"]
+    for r in rows[2:]:
+        out.append(f"## {r[hdr.index('Kernel Name')]}")
+        for m in METRICS:
+            if m in hdr:
+                out.append(f"{m:75s} {r[hdr.index(m)]}  {rows[1][hdr.index(m)]}")
+    (OUT / f"{tag}_ncu_{which}.txt").write_text("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    OUT.mkdir(exist_ok=True)
+    launches(tag)
+    for which in ("fwd", "bwd"):
+        full(tag, which)
+    for name in ("bench.json", "bench_ref.json", "smoke.log", "pytest_gpu.log"):
+        src = ROOT / "gpurun_out" / f"{tag}_{name}"
+        if src.exists():
+            (OUT / f"{tag}_{name}").write_text(src.read_text())
+    print("wrote", sorted(p.name for p in OUT.glob(f"{tag}_*")))
