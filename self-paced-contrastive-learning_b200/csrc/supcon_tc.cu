@@ -63,6 +63,7 @@ struct Params {
   float* dz;
   int64_t lddz;
   unsigned long long* trace;   // debug timeline (CTA 0), normally nullptr
+  int dbg;                     // debug experiment switches (tools/gpu_trace.py), normally 0
 };
 
 // debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
@@ -317,11 +318,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
           const uint32_t ph = (it / p.nslot) & 1;
           mbar_wait(&bar->empty[slot], ph ^ 1);
           TRACE(0, it, 0);
+          if (p.dbg & 4) {
+            mbar_arrive(&bar->full[slot]);
+          } else {
           mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
           uint8_t* dst = sm.slot(slot);
           for (int c = 0; c < p.dc; ++c)
             tma_load_2d(dst + c * CHUNK_BYTES, &tmap, &bar->full[slot], c * 64, static_cast<int32_t>(t * TILE));
           bulk_load_1d(sm.slot_labels(slot), p.labels + t * TILE, META_LABEL_BYTES, &bar->full[slot]);
+          }
         }
         ++it;
       });
@@ -412,20 +417,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
           uint32_t va[32], vb[32];
+          if (p.dbg & 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) va[e] = vb[e] = 0;
+          }
+          if (!(p.dbg & 2)) {
           tmem_ld_32x32b_x32(taddr, va);
           tmem_wait_ld();
+          }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             uint32_t(&cur)[32] = (ch & 1) ? vb : va;
             uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
+            if (ch < 3 && !(p.dbg & 2)) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
             if (PASS == 0) {
-              if (!slow) stats_chunk_fast(cur, c2c2, nc2nc2, acc2);
+              if (p.dbg & 1) { acc2[ch] ^= cur[ch]; }
+              else if (!slow) stats_chunk_fast(cur, c2c2, nc2nc2, acc2);
               else stats_chunk_slow(cur, ch, j0, gi, p.N, li, lab_s, c2, s0, cnt, spx);
             } else {
               sp_chunk(cur, ch, j0, gi, p.N, li, lab_s, p, logD, s0, s1);
             }
-            if (ch < 3) tmem_wait_ld();
+            if (ch < 3 && !(p.dbg & 2)) tmem_wait_ld();
           }
           tc_fence_before();
           __syncwarp();
@@ -781,6 +793,7 @@ static int pick_slots(int dc) {
 }
 
 static unsigned long long* g_trace = nullptr;
+static int g_dbg = 0;
 
 static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad, const int32_t* labels,
                        const int32_t* sig, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
@@ -812,6 +825,7 @@ static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad,
   p.inv_gamma = gamma > 0.f ? 1.f / gamma : 0.f;
   p.mode = mode;
   p.trace = g_trace;
+  p.dbg = g_dbg;
   return SPCL_OK;
 }
 
@@ -899,6 +913,10 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
 }
 
 // debug only (not part of include/spcl.h): device buffer of 4 roles x 64 tiles x 4 events x u64, or NULL
+extern "C" int spcl_debug_set_flags(int flags) {
+  tc::g_dbg = flags;
+  return SPCL_OK;
+}
 extern "C" int spcl_debug_set_trace(void* buf) {
   tc::g_trace = static_cast<unsigned long long*>(buf);
   return SPCL_OK;
