@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _PKG_DIR = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libspcl_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("SPCL_B200_LIB", _PKG_DIR / "libspcl_b200.so"))   # override: kernel A/B builds
 BUILD_SCRIPT = _PKG_DIR / "csrc" / "build.sh"
 
 MODE_NONE, MODE_HARD, MODE_SOFT = 0, 1, 2

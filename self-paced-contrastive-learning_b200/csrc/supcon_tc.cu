@@ -1,26 +1,36 @@
 // Tensor-core path of the fused self-paced SupCon loss for sm_100a (B200).
 //
-// S = Z Z^T is produced 128 x 128 tile by tile with tcgen05.mma (bf16 operands staged by TMA into
-// 128B-swizzled shared memory, fp32 accumulators in TMEM) and consumed straight out of TMEM by the
-// epilogue warps; the N x N matrix never exists in HBM.
+// S = Z Z^T is produced tile by tile with tcgen05.mma (bf16 operands staged by TMA into 128B-swizzled
+// shared memory, fp32 accumulators in TMEM) and consumed straight out of TMEM by the epilogue warps;
+// the N x N matrix never exists in HBM.
 //
-//   fwd_kernel<0>  "stats" : rowsum_i = sum_{j != i} exp(S_ij - 1/tau), c_i, sum_j P_ij <z_i, z_j>
-//                            (contrast_loss3.py:25-31, :157-167, :180-182)
-//   fwd_kernel<1>  "sp"    : sum_j P W LLH, sum_j P W with W from the final logD_i; only tiles that can
-//                            hold positives are computed at all (:184-197, :207-214)
-//   row_finalize           : row_stats planes {logD, 1/c, A, u} and the three partial sums
-//   bwd_kernel             : per tile  S -> T = M E (u_i + u_j) - P (W_ij/c_i + W_ji/c_j)  (bf16, written
-//                            back into TMEM over S) and a second tcgen05.mma  dZ_I += T_IJ Z_J  whose
-//                            A operand is read from TMEM and whose B operand is the same Z_J tile read
-//                            MN-major; dZ lives in TMEM until the row block is finished.
+//   stats_kernel<BN> : rowsum_i = sum_{j != i} exp(S_ij - 1/tau), c_i, sum_j P_ij <z_i, z_j>
+//                      (contrast_loss3.py:25-31, :157-167, :180-182).  128 x BN tiles; BN = 256 keeps the
+//                      single-CTA S GEMM off the shared-memory operand-read limit (691 vs ~1000 cycles
+//                      per 128 x 128 block, tools/mma_bench2.cu).
+//   sp_kernel        : sum_j P W LLH, sum_j P W with W from the final logD_i; only tiles that can hold
+//                      positives are computed at all (:184-197, :207-214)
+//   row_finalize     : row_stats planes {logD, 1/c, A, u} and the three partial sums
+//   bwd_kernel       : per tile  S -> T = M E (u_i + u_j) - P (W_ij/c_i + W_ji/c_j)  (bf16, written back
+//                      into TMEM over S) and a second tcgen05.mma  dZ_I += T_IJ Z_J  whose A operand is
+//                      read from TMEM and whose B operand is the same Z_J tile read MN-major; dZ lives in
+//                      TMEM until the row block is finished.
 //
 // Work decomposition: the (row block, column tile) grid is flattened and cut into gridDim.x equal
 // contiguous ranges (one persistent CTA per SM), so any N balances to +-1 tile; partial row results are
-// combined with atomics.  Warp roles: 0..7 = two epilogue warpgroups that alternate tiles,
-// 8 = TMA producer, 9 and 11 = MMA issuers, 10 = TMEM allocator.
+// combined with atomics.  Warp roles: 0..7 = two epilogue warpgroups, 8 = TMA producer, 9 = MMA issuer,
+// 10 = TMEM allocator (11 = second issuer of the sparse sp_kernel only).
 //
-// Epilogue arithmetic runs two lanes per issue slot (FFMA2 / FADD2 / FMUL2) and the TMEM loads are
-// double buffered; the MUFU (ex2) pipe is the binding unit of both big kernels.
+// What the timeline experiments showed (tools/gpu_exp.py, tools/mma_bench2.cu) and this file is built on:
+//   * tcgen05.mma issue blocks while the tensor pipe's short queue is full, so "issue time" is execution
+//     time; a group of MMAs that starts on an idle pipe pays ~250 extra cycles of fill latency.  One
+//     issuer warp therefore streams ALL groups back to back in program order, with the operands of the
+//     next tiles already resident (slots are released by the MMA commit alone; the epilogue never holds a
+//     shared-memory slot in the stats kernel).
+//   * the MUFU pipe (16 ex2 / clk / SM = 1024 cycles per 128 x 128 block) was the binding unit of every
+//     epilogue; a compile-time fraction of the exponentials is evaluated on the FMA pipe instead
+//     (Cody-Waite split + polynomial, two lanes per FFMA2), balancing the two pipes.
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -43,19 +53,31 @@ constexpr int kMaxBufs = 4;
 constexpr uint32_t kTmemCols = 512;
 constexpr unsigned kFullMask = 0xffffffffu;
 // Warp roles.  The issue arbiter favours the highest warp id of an SMSP, so the single-thread TMA and MMA
-// issuers sit ABOVE the eight MUFU-heavy epilogue warps; as low warp ids they were starved of issue slots
-// (measured: ~100 cycles per tcgen05.mma issue, the MMA thread became the bottleneck of both kernels).
+// issuers sit ABOVE the eight MUFU-heavy epilogue warps.
 constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp = 10, kMmaWarp1 = 11;
+
+// pairs (of the 16 per 32-column chunk) whose exponential runs on the FMA pipe
+#ifndef SPCL_FWD_POLY_PAIRS
+#define SPCL_FWD_POLY_PAIRS 7
+#endif
+#ifndef SPCL_BWD_POLY_PAIRS
+#define SPCL_BWD_POLY_PAIRS 5
+#endif
 
 struct Params {
   int64_t N, n_pad;
   int64_t row_begin, row_end;
-  int64_t CT, RB;
+  int64_t CT, RB;              // column tiles of THIS launch's tile width, row blocks
+  int64_t CT128;               // n_pad / 128
   int d_pad, dc, nslot, nbuf, d;
   const int32_t* labels;
   const int4* sig;
   float inv_tau, gamma, inv_gamma;
   int mode;
+  // exp(S - 1/tau) = 2^(dot * c2 - c2):  c2 = ci + cf;  ex_magic = 1.5 * 2^23 - ci;  pf / pb = minimax
+  // coefficients of 2^f on [-0.5, 0.5] (degree 4 / 3) pre-multiplied by 2^-cf
+  float c2, ex_magic;
+  float pf[5], pb[4];
   float4* acc;               // fwd scratch  [n_pad] {rowsum, c, sum P dot | sum P W LLH, sum P W}
   const float* row_stats;    // bwd          4 planes of n_pad floats: logD | 1/c | A | u
   const float* scalars;
@@ -63,7 +85,7 @@ struct Params {
   float* dz;
   int64_t lddz;
   unsigned long long* trace;   // debug timeline (CTA 0), normally nullptr
-  int dbg;                     // debug experiment switches (tools/gpu_trace.py), normally 0
+  int dbg;                     // debug experiment switches (tools/gpu_exp.py), normally 0
 };
 
 // debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
@@ -99,19 +121,20 @@ struct SmemView {
   }
 };
 
-__host__ __device__ inline size_t smem_payload_bytes(int dc, int nslot) {
-  return static_cast<size_t>(dc) * CHUNK_BYTES * (1 + nslot) + static_cast<size_t>(nslot) * META_BYTES +
-         sizeof(Barriers);
+// bn = column-tile width (rows of Z per slot); meta = per-slot labels + column statistics staged by bulk copy
+__host__ __device__ inline size_t smem_payload_bytes(int dc, int nslot, int bn, bool meta) {
+  return static_cast<size_t>(dc) * CHUNK_BYTES + static_cast<size_t>(nslot) * dc * bn * 128 +
+         (meta ? static_cast<size_t>(nslot) * META_BYTES : 0) + sizeof(Barriers);
 }
 
-__device__ __forceinline__ SmemView carve(uint8_t* raw, const Params& p) {
+__device__ __forceinline__ SmemView carve(uint8_t* raw, const Params& p, int bn, bool meta) {
   SmemView v;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  v.slot_bytes = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
+  v.slot_bytes = static_cast<uint32_t>(p.dc) * bn * 128;
   v.a_tile = base;
-  v.slots = base + v.slot_bytes;
+  v.slots = base + static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
   v.meta = v.slots + static_cast<size_t>(p.nslot) * v.slot_bytes;
-  v.bar = reinterpret_cast<Barriers*>(v.meta + static_cast<size_t>(p.nslot) * META_BYTES);
+  v.bar = reinterpret_cast<Barriers*>(v.meta + (meta ? static_cast<size_t>(p.nslot) * META_BYTES : 0));
   return v;
 }
 
@@ -126,24 +149,49 @@ __device__ __forceinline__ void cta_range(const Params& p, int64_t& f0, int64_t&
   f1 = total * (blockIdx.x + 1) / gridDim.x;
 }
 
-// Calls f(t) for every column tile of [tb, te) this pass has to visit, in order, warp-uniformly.
-// PASS 1 visits only tiles whose label signature can match the row block's; 32 candidates are tested
-// per step (one per lane) so the scan costs one L2 round trip per 32 tiles instead of one per tile.
-template <int PASS, typename F>
-__device__ __forceinline__ void for_each_tile(const Params& p, const int4& rsig, int64_t tb, int64_t te, int lane,
-                                              F&& f) {
-  if (PASS == 0) {
-    for (int64_t t = tb; t < te; ++t) f(t);
-  } else {
-    for (int64_t base = tb; base < te; base += 32) {
-      const int64_t t = base + lane;
-      const bool act = (t < te) && sig_overlap(rsig, p.sig[t]);
-      unsigned m = __ballot_sync(kFullMask, act);
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        f(base + b);
-      }
+// Walks the CTA's flattened tile range one tile at a time; a "segment" is the part of one row block.
+// 32-bit state: the per-tile bookkeeping of the single-thread roles sits on the critical path.
+struct TileCursor {
+  uint32_t t, CT, it, n, seg;
+  __device__ __forceinline__ TileCursor(int64_t f0, int64_t f1, int64_t ct)
+      : t(static_cast<uint32_t>(f0 % ct)), CT(static_cast<uint32_t>(ct)), it(0), n(static_cast<uint32_t>(f1 - f0)),
+        seg(0) {}
+  __device__ __forceinline__ bool valid() const { return it < n; }
+  __device__ __forceinline__ bool first() const { return it == 0 || t == 0; }
+  __device__ __forceinline__ bool last() const { return it + 1 == n || t + 1 == CT; }
+  __device__ __forceinline__ void next() {
+    if (last()) ++seg;
+    ++it;
+    if (++t == CT) t = 0;
+  }
+};
+
+// position in a ring of n buffers and the mbarrier phase parity of the current lap
+struct Ring {
+  uint32_t idx, ph, n;
+  __device__ __forceinline__ explicit Ring(uint32_t n_) : idx(0), ph(0), n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++idx == n) {
+      idx = 0;
+      ph ^= 1;
+    }
+  }
+};
+
+// Calls f(t) for every column tile of [tb, te) the sp pass has to visit, in order, warp-uniformly: only
+// tiles whose label signature can match the row block's; 32 candidates are tested per step (one per lane)
+// so the scan costs one L2 round trip per 32 tiles instead of one per tile.
+template <typename F>
+__device__ __forceinline__ void for_each_pos_tile(const Params& p, const int4& rsig, int64_t tb, int64_t te, int lane,
+                                                  F&& f) {
+  for (int64_t base = tb; base < te; base += 32) {
+    const int64_t t = base + lane;
+    const bool act = (t < te) && sig_overlap(rsig, p.sig[t]);
+    unsigned m = __ballot_sync(kFullMask, act);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      f(base + b);
     }
   }
 }
@@ -166,43 +214,95 @@ __device__ __forceinline__ void init_barriers(Barriers* b, int slot_consumers, i
   fence_mbar_init();
 }
 
-// S_tile(tmem col) (+)= A_tile(smem, K-major) * B_slot(smem, K-major)^T for the K = 16 steps [k0, k1)
-// (step kk lives in 128B-swizzle panel kk / 4 at byte offset (kk % 4) * 32; step 0 overwrites D)
+// S_tile(tmem col) (+)= A_tile(smem, K-major) * B_slot(smem, K-major)^T for the K = 16 steps [0, nk)
+// (step kk lives in 128B-swizzle panel kk / 4 at byte offset (kk % 4) * 32; step 0 overwrites D).
+// BN = rows of the B slot = N of the instruction; a B panel is BN rows x 128 B.
+template <int BN>
 __device__ __forceinline__ void issue_s_mma(uint32_t d_tmem, uint32_t a_base, uint32_t b_base, int k0, int k1) {
-  constexpr uint32_t idesc = make_idesc_bf16(TILE, TILE, false, false);
+  constexpr uint32_t idesc = make_idesc_bf16(TILE, BN, false, false);
   for (int kk = k0; kk < k1; ++kk) {
-    const uint32_t off = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
-    mma_ss(d_tmem, make_smem_desc_sw128(a_base + off, 16, 1024), make_smem_desc_sw128(b_base + off, 16, 1024), idesc,
+    const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
+    const uint32_t pb = static_cast<uint32_t>(kk >> 2) * (BN * 128) + static_cast<uint32_t>(kk & 3) * 32;
+    mma_ss(d_tmem, make_smem_desc_sw128(a_base + pa, 16, 1024), make_smem_desc_sw128(b_base + pb, 16, 1024), idesc,
            kk != 0 ? 1u : 0u);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
+// exponentials: E = exp(S - 1/tau) = 2^(dot * c2 - c2)
+// ---------------------------------------------------------------------------------------------
+struct ExpK {
+  uint64_t c2, nc2, mg, neg1;
+  uint64_t c[5];
+};
+
+template <int DEG>
+__device__ __forceinline__ ExpK make_expk(const Params& p) {
+  ExpK k;
+  k.c2 = pack_f32x2(p.c2, p.c2);
+  k.nc2 = pack_f32x2(-p.c2, -p.c2);
+  k.mg = pack_f32x2(p.ex_magic, p.ex_magic);
+  k.neg1 = pack_f32x2(-1.f, -1.f);
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) {
+    const float c = (DEG == 4) ? p.pf[i] : p.pb[i];
+    k.c[i] = pack_f32x2(c, c);
+  }
+  if (DEG < 4) k.c[4] = 0ull;
+  return k;
+}
+
+// MUFU pipe: two ex2.approx
+__device__ __forceinline__ uint64_t ex2_mufu2(uint64_t d2, const ExpK& k) {
+  float x0, x1;
+  unpack_f32x2(fma_f32x2(d2, k.c2, k.nc2), x0, x1);
+  return pack_f32x2(ex2_approx(x0), ex2_approx(x1));
+}
+
+// FMA pipe: y = dot * c2;  t = y + (magic - ci) leaves round(y) - ci in the low mantissa bits;  f = y - round(y);
+// 2^(y - c2) = poly(f) with the exponent field advanced by round(y) - ci (one shift-add on the ALU pipe).
+template <int DEG>
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t d2, const ExpK& k) {
+  const uint64_t t = fma_f32x2(d2, k.c2, k.mg);
+  const uint64_t nn = fma_f32x2(t, k.neg1, k.mg);       // -(round(y)), exact
+  const uint64_t f = fma_f32x2(d2, k.c2, nn);
+  uint64_t q = fma_f32x2(f, k.c[DEG], k.c[DEG - 1]);
+#pragma unroll
+  for (int i = DEG - 2; i >= 0; --i) q = fma_f32x2(q, f, k.c[i]);
+  const uint32_t q0 = static_cast<uint32_t>(q), q1 = static_cast<uint32_t>(q >> 32);
+  const uint32_t t0 = static_cast<uint32_t>(t), t1 = static_cast<uint32_t>(t >> 32);
+  return pack_u32x2(q0 + (t0 << 23), q1 + (t1 << 23));
+}
+
+// evenly spread `npoly` of the 16 pairs of a chunk
+__host__ __device__ constexpr bool use_poly(int pair, int npoly) {
+  return ((pair + 1) * npoly) / 16 != (pair * npoly) / 16;
+}
+
+// ---------------------------------------------------------------------------------------------
 // epilogue chunk bodies: 32 consecutive S columns of this thread's row
 // ---------------------------------------------------------------------------------------------
-// fast: every column is a valid negative.  acc[k] += exp2(dot * c2 - c2), two lanes per instruction.
-__device__ __forceinline__ void stats_chunk_fast(const uint32_t (&v)[32], uint64_t c2c2, uint64_t nc2nc2,
-                                                 uint64_t (&acc)[4]) {
+// fast: every column is a valid negative.  acc[k] += E, two lanes per instruction.
+__device__ __forceinline__ void stats_chunk_fast(const uint32_t (&v)[32], const ExpK& k, uint64_t (&acc)[4]) {
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
-    const uint64_t x = fma_f32x2(pack_u32x2(v[e], v[e + 1]), c2c2, nc2nc2);
-    float x0, x1;
-    unpack_f32x2(x, x0, x1);
-    acc[(e >> 1) & 3] = add_f32x2(acc[(e >> 1) & 3], pack_f32x2(ex2_approx(x0), ex2_approx(x1)));
+    const uint64_t d2 = pack_u32x2(v[e], v[e + 1]);
+    const uint64_t ex = use_poly(e >> 1, SPCL_FWD_POLY_PAIRS) ? ex2_poly2<4>(d2, k) : ex2_mufu2(d2, k);
+    acc[(e >> 1) & 3] = add_f32x2(acc[(e >> 1) & 3], ex);
   }
 }
 
-// slow: diagonal / tail / tiles that may hold positives
-__device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch, int64_t j0, int64_t gi, int64_t N,
-                                                 int li, const int32_t* lab_s, float c2, float& rowsum, float& cnt,
-                                                 float& spx) {
+// slow: diagonal / tail / tiles that may hold positives.  jdiag = column of this row's diagonal element inside
+// the 128-column block (or -1), jmax = number of valid columns, lab = labels of the block's columns (global).
+__device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
+                                                 const int32_t* __restrict__ lab, float c2, float& rowsum,
+                                                 float& cnt, float& spx) {
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
     const int cidx = ch * 32 + e;
-    const int64_t j = j0 + cidx;
     const float dot = __uint_as_float(v[e]);
-    const bool valid = (j < N) && (j != gi);
-    const bool pos = valid && (lab_s[cidx] == li);
+    const bool valid = (cidx < jmax) && (cidx != jdiag);
+    const bool pos = valid && (__ldg(lab + cidx) == li);
     const float ex = ex2_approx(fmaf(dot, c2, -c2));
     rowsum += valid ? ex : 0.f;
     cnt += pos ? 1.f : 0.f;
@@ -210,14 +310,13 @@ __device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch
   }
 }
 
-__device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int64_t j0, int64_t gi, int64_t N, int li,
+__device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
                                          const int32_t* lab_s, const Params& p, float logD, float& wl, float& wp) {
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
     const int cidx = ch * 32 + e;
-    const int64_t j = j0 + cidx;
     const float dot = __uint_as_float(v[e]);
-    const bool pos = (j < N) && (j != gi) && (lab_s[cidx] == li);
+    const bool pos = (cidx < jmax) && (cidx != jdiag) && (lab_s[cidx] == li);
     const float l = fmaf(-dot, p.inv_tau, logD);          // l_ij = logD_i - S_ij
     const float w = pos ? sp_weight(l, p.gamma, p.inv_gamma, p.mode) : 0.f;
     wl = fmaf(w, -l, wl);
@@ -225,19 +324,15 @@ __device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int64_
   }
 }
 
-// fast: T = exp2(dot * c2 - c2) * (u_i + u_j), packed to bf16 pairs
-__device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&v)[32], const float* u_s, uint64_t c2c2,
-                                               uint64_t nc2nc2, uint64_t uiui, uint32_t (&pk)[16]) {
+// fast: T = E * (u_i + u_j), packed to bf16 pairs
+__device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&v)[32], const float* u_s, const ExpK& k, uint64_t uiui,
+                                               uint32_t (&pk)[16]) {
 #pragma unroll
   for (int e = 0; e < 32; e += 4) {
     const float4 uj = *reinterpret_cast<const float4*>(u_s + e);
-    const uint64_t xa = fma_f32x2(pack_u32x2(v[e], v[e + 1]), c2c2, nc2nc2);
-    const uint64_t xb = fma_f32x2(pack_u32x2(v[e + 2], v[e + 3]), c2c2, nc2nc2);
-    float x0, x1, x2, x3;
-    unpack_f32x2(xa, x0, x1);
-    unpack_f32x2(xb, x2, x3);
-    const uint64_t ea = pack_f32x2(ex2_approx(x0), ex2_approx(x1));
-    const uint64_t eb = pack_f32x2(ex2_approx(x2), ex2_approx(x3));
+    const uint64_t da = pack_u32x2(v[e], v[e + 1]), db = pack_u32x2(v[e + 2], v[e + 3]);
+    const uint64_t ea = use_poly(e >> 1, SPCL_BWD_POLY_PAIRS) ? ex2_poly2<3>(da, k) : ex2_mufu2(da, k);
+    const uint64_t eb = use_poly((e >> 1) + 1, SPCL_BWD_POLY_PAIRS) ? ex2_poly2<3>(db, k) : ex2_mufu2(db, k);
     const uint64_t ta = mul_f32x2(ea, add_f32x2(pack_f32x2(uj.x, uj.y), uiui));
     const uint64_t tb = mul_f32x2(eb, add_f32x2(pack_f32x2(uj.z, uj.w), uiui));
     float t0, t1, t2, t3;
@@ -248,26 +343,34 @@ __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&v)[32], const fl
   }
 }
 
-__device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, int64_t j0, int64_t gi, int64_t N,
-                                               int li, const int32_t* lab_s, const float* logD_s,
-                                               const float* invc_s, const float* u_s, const Params& p, float c2,
-                                               float logD_i, float invc_i, float u_i, uint32_t (&pk)[16]) {
+template <int MODE>
+__device__ __forceinline__ float sp_w(float l, float gamma, float inv_gamma) {
+  if (MODE == SPCL_MODE_HARD) return l <= gamma ? 1.f : 0.f;
+  if (MODE == SPCL_MODE_SOFT) return fmaxf(1.f - l * inv_gamma, 0.f);
+  return 1.f;
+}
+
+// slow (branch free): T = valid E (u_i + u_j) - pos (W_ij / c_i + W_ji / c_j)
+template <int MODE>
+__device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
+                                               const int32_t* lab_s, const float* logD_s, const float* invc_s,
+                                               const float* u_s, const Params& p, float logD_i, float invc_i,
+                                               float u_i, uint32_t (&pk)[16]) {
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
     float tv[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int cidx = ch * 32 + e + h;
-      const int64_t j = j0 + cidx;
       const float dot = __uint_as_float(v[e + h]);
-      const bool valid = (j < N) && (j != gi);
-      const float ex = ex2_approx(fmaf(dot, c2, -c2));
+      const bool valid = (cidx < jmax) && (cidx != jdiag);
+      const bool pos = valid && (lab_s[cidx] == li);
+      const float ex = ex2_approx(fmaf(dot, p.c2, -p.c2));
+      const float s = dot * p.inv_tau;
+      const float w = sp_w<MODE>(logD_i - s, p.gamma, p.inv_gamma) * invc_i +
+                      sp_w<MODE>(logD_s[cidx] - s, p.gamma, p.inv_gamma) * invc_s[cidx];
       float t = valid ? ex * (u_i + u_s[cidx]) : 0.f;
-      if (valid && lab_s[cidx] == li) {
-        const float s = dot * p.inv_tau;
-        t -= sp_weight(logD_i - s, p.gamma, p.inv_gamma, p.mode) * invc_i +
-             sp_weight(logD_s[cidx] - s, p.gamma, p.inv_gamma, p.mode) * invc_s[cidx];
-      }
+      t -= pos ? w : 0.f;
       tv[h] = t;
     }
     pk[e >> 1] = pack_bf16x2(tv[0], tv[1]);
@@ -275,12 +378,211 @@ __device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, 
 }
 
 // =================================================================================================
-// forward
+// forward, pass A: row statistics over all column tiles
 // =================================================================================================
-template <int PASS>
-__global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                            const __grid_constant__ CUtensorMap tmap_b, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const SmemView sm = carve(smem_raw, p);
+  const SmemView sm = carve(smem_raw, p, BN, false);
+  Barriers* bar = sm.bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kSub = BN / TILE;                    // 128-column blocks per tile
+  constexpr int kBufs = static_cast<int>(kTmemCols) / BN;
+
+  if (warp == kMmaWarp0 && lane == 0)
+    init_barriers(bar, /*slot: MMA commit*/ 1, /*S buffer: epilogue warps that read it*/ kSub == 2 ? 8 : 4,
+                  /*a_empty*/ 1);
+  if (warp == kAllocWarp) tmem_alloc<kTmemCols>(&bar->tmem_base);
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_base;
+  const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
+
+  int64_t f0, f1;
+  cta_range(p, f0, f1);
+  const int64_t rb0 = p.row_begin / TILE, I0 = f0 / p.CT;
+  const uint32_t a_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
+  const uint32_t slot_tx = static_cast<uint32_t>(p.dc) * BN * 128;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      Ring rs(p.nslot);
+      for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next()) {
+        if (c.first()) {
+          const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
+          mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
+          mbar_arrive_expect_tx(&bar->a_full, a_tx);
+          for (int k = 0; k < p.dc; ++k) tma_load_2d(sm.a_tile + k * CHUNK_BYTES, &tmap_a, &bar->a_full, k * 64, gi0);
+        }
+        const int slot = rs.idx;
+        mbar_wait(&bar->empty[slot], rs.ph ^ 1);
+        TRACE(0, c.it, 0);
+        if (p.dbg & 4) {
+          mbar_arrive(&bar->full[slot]);
+        } else {
+          mbar_arrive_expect_tx(&bar->full[slot], slot_tx);
+          uint8_t* dst = sm.slot(slot);
+          for (int k = 0; k < p.dc; ++k)
+            tma_load_2d(dst + k * (BN * 128), &tmap_b, &bar->full[slot], k * 64, static_cast<int32_t>(c.t * BN));
+        }
+      }
+    }
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
+    // ------------------------------- MMA issuers --------------------------------
+    // tcgen05.mma issue blocks while the tensor pipe's short queue is full, so the issuing thread gets the
+    // pipe back only one or two MMAs before it runs dry; its own per-tile software path (barrier round trips
+    // cost 100-300 cycles each) does not fit in that slack.  Two issuer warps therefore alternate tiles: while
+    // one is blocked issuing tile t, the other has already waited for the operands of tile t + 1 and only
+    // needs the "turn" (a named-barrier handoff, passed when the last MMA of tile t has been issued), so the
+    // groups enter the pipe back to back and strictly in tile order.
+    // The whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers -- a
+    // lane-0-only loop made the compiler wrap every tcgen05.mma in an ELECT / R2UR waterfall loop); lane 0
+    // polls, the elect.sync lane issues.
+    const uint32_t mw = (warp == kMmaWarp0) ? 0u : 1u;
+    const uint32_t a_base = smem_u32(sm.a_tile);
+    const int nk = p.dc * 4;
+    Ring rs(p.nslot), rb(kBufs);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next(), rb.next()) {
+      if ((c.it & 1) != mw) continue;
+      if (lane == 0) {
+        if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
+        mbar_wait(&bar->full[rs.idx], rs.ph);
+        mbar_wait(&bar->s_empty[rb.idx], rb.ph ^ 1);
+      }
+      __syncwarp();
+      if (c.it != 0) named_bar_sync(1 + mw, 64);              // tile it - 1 has been issued
+      TRACE(1, c.it, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_s_mma<BN>(tmem_u + rb.idx * BN, a_base, smem_u32(sm.slot(rs.idx)), 0, nk);
+        tc_commit(&bar->empty[rs.idx]);
+        tc_commit(&bar->s_full[rb.idx]);
+        if (c.last()) tc_commit(&bar->a_empty);
+      }
+      __syncwarp();
+      if (c.it + 1 < c.n) named_bar_arrive(1 + (mw ^ 1), 64);  // the other warp may issue tile it + 1
+      TRACE(1, c.it, 1);
+    }
+  } else if (warp < kEpilogueWarps) {
+    // ------------------------------- epilogue -----------------------------------
+    // BN = 256: both warpgroups work on every tile, one 128-column block each.  BN = 128: they alternate tiles.
+    const int wg = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const ExpK ek = make_expk<4>(p);
+    int64_t gi0 = 0, gi = 0;
+    bool row_ok = false;
+    int li = 0;
+    int4 rsig = make_int4(0, 0, 0, 0);
+    uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};       // fast path: packed partial row sums
+    float s0 = 0.f, cnt = 0.f, spx = 0.f;              // slow path: rowsum, positives, sum P dot
+
+    // 128-column block this warpgroup handles in column tile t, and the tile it handles after tile t
+    auto block_of = [&](uint32_t t) -> int64_t { return static_cast<int64_t>(t) * kSub + (kSub == 2 ? wg : 0); };
+    auto tile_after = [&](uint32_t t) -> uint32_t {
+      uint32_t t2 = t + (kSub == 2 ? 1u : 2u);
+      while (t2 >= static_cast<uint32_t>(p.CT)) t2 -= static_cast<uint32_t>(p.CT);
+      return t2;
+    };
+    auto load_sig = [&](uint32_t t) -> int4 { return p.sig[min(block_of(t), p.CT128 - 1)]; };
+    Ring rb(kBufs);
+    TileCursor c0(f0, f1, p.CT);
+    // the signature of the NEXT block is requested one tile ahead: a dependent L2 round trip per tile was
+    // ~700 exposed cycles in front of every epilogue
+    int4 nsig = load_sig(c0.t + ((kSub == 1 && wg == 1) ? 1u : 0u) < static_cast<uint32_t>(p.CT)
+                             ? c0.t + ((kSub == 1 && wg == 1) ? 1u : 0u) : 0u);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rb.next()) {
+      if (c.first()) {
+        gi0 = p.row_begin + (I0 + c.seg) * TILE;
+        gi = gi0 + r;
+        row_ok = gi < p.row_end;
+        li = row_ok ? p.labels[gi] : 0;
+        rsig = p.sig[rb0 + I0 + c.seg];
+      }
+      const bool mine = (kSub == 2) || (static_cast<int>(c.it & 1) == wg);
+      if (mine) {
+        const int buf = rb.idx;
+        const uint32_t bph = rb.ph;
+        const int64_t jb = block_of(c.t);
+        const int64_t j0 = jb * TILE;
+        const bool inside = jb < p.CT128;
+        const int4 csig = nsig;
+        nsig = load_sig(tile_after(c.t));
+        bool slow = true;
+        if (inside) {
+          const bool diag = (j0 < gi0 + TILE) && (gi0 < j0 + TILE);
+          const bool tail = (j0 + TILE) > p.N;
+          slow = diag || tail || sig_overlap(rsig, csig);
+        }
+        mbar_wait(&bar->s_full[buf], bph);
+        TRACE(2 + wg, c.it, 0);
+        tc_fence_after();
+        if (inside && !(p.dbg & 2)) {
+          const int64_t dj = gi - j0;
+          const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+          const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
+          const int32_t* lab = p.labels + j0;
+          const uint32_t taddr = lane_base + buf * BN + (kSub == 2 ? wg * TILE : 0);
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(taddr, va);
+          tmem_wait_ld();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+            uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
+            if (p.dbg & 1) acc2[ch] ^= cur[ch];
+            else if (!slow) stats_chunk_fast(cur, ek, acc2);
+            else stats_chunk_slow(cur, ch, jdiag, jmax, li, lab, p.c2, s0, cnt, spx);
+            if (ch < 3) tmem_wait_ld();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->s_empty[buf]);
+        TRACE(2 + wg, c.it, 1);
+      }
+      if (c.last()) {
+        if (row_ok) {
+          float* a = reinterpret_cast<float*>(p.acc + gi);
+          float lo, hi, rowsum = s0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            unpack_f32x2(acc2[k], lo, hi);
+            rowsum += lo + hi;
+          }
+          if (rowsum != 0.f) atomicAdd(a + 0, rowsum);
+          if (cnt != 0.f) atomicAdd(a + 1, cnt);
+          if (p.mode == SPCL_MODE_NONE && spx != 0.f) atomicAdd(a + 2, spx);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc2[k] = 0ull;
+        s0 = cnt = spx = 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kAllocWarp) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// forward, pass B: self-paced sums over the tiles that can hold positives (128 x 128 tiles)
+// =================================================================================================
+__global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sm = carve(smem_raw, p, TILE, true);
   Barriers* bar = sm.bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -291,7 +593,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bar->tmem_base;
-  const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
+  const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
 
   int64_t f0, f1;
   cta_range(p, f0, f1);
@@ -299,7 +601,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
   const uint32_t tile_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES + META_LABEL_BYTES;
 
   if (warp == kProducerWarp) {
-    // ------------------------------- TMA producer -------------------------------
     uint32_t it = 0, seg = 0;
     for (int64_t f = f0; f < f1; ++seg) {
       const int64_t I = f / p.CT, tb = f % p.CT;
@@ -312,34 +613,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
         for (int c = 0; c < p.dc; ++c) tma_load_2d(sm.a_tile + c * CHUNK_BYTES, &tmap, &bar->a_full, c * 64, gi0);
       }
       const int4 rsig = p.sig[rb0 + I];
-      for_each_tile<PASS>(p, rsig, tb, te, lane, [&](int64_t t) {
+      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t t) {
         if (lane == 0) {
           const int slot = it % p.nslot;
           const uint32_t ph = (it / p.nslot) & 1;
           mbar_wait(&bar->empty[slot], ph ^ 1);
-          TRACE(0, it, 0);
-          if (p.dbg & 4) {
-            mbar_arrive(&bar->full[slot]);
-          } else {
           mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
           uint8_t* dst = sm.slot(slot);
           for (int c = 0; c < p.dc; ++c)
             tma_load_2d(dst + c * CHUNK_BYTES, &tmap, &bar->full[slot], c * 64, static_cast<int32_t>(t * TILE));
           bulk_load_1d(sm.slot_labels(slot), p.labels + t * TILE, META_LABEL_BYTES, &bar->full[slot]);
-          }
         }
         ++it;
       });
       __syncwarp();
     }
   } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
-    // ------------------------------- MMA issuers --------------------------------
-    // Two issuer warps alternate tiles.  tcgen05.mma issue blocks while the tensor pipe's short queue is
-    // full and an mbarrier probe costs 150-350 cycles, so a single issuer left the pipe idle between tiles
-    // (measured: 780 cycles issuing + ~880 cycles of waits per tile); with two, one warp's barrier round
-    // trips overlap the other's blocking issue.  The whole warp runs the loop (warp-uniform control flow
-    // keeps the descriptors in uniform registers -- a lane-0-only loop made the compiler wrap every
-    // tcgen05.mma in an ELECT / R2UR waterfall loop); lane 0 polls, the elect.sync lane issues.
+    // two issuer warps alternate tiles (the visited tiles are sparse: latency, not throughput, matters here)
     const uint32_t mw = (warp == kMmaWarp0) ? 0u : 1u;
     uint32_t it = 0, seg = 0;
     const uint32_t a_base = smem_u32(sm.a_tile);
@@ -351,7 +641,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
       if (lane == 0) mbar_wait(&bar->a_full, seg & 1);
       __syncwarp();
       const int4 rsig = p.sig[rb0 + I];
-      for_each_tile<PASS>(p, rsig, tb, te, lane, [&](int64_t) {
+      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t) {
         if ((it & 1) == mw) {
           const int slot = it % p.nslot, buf = it % p.nbuf;
           const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
@@ -360,15 +650,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
             mbar_wait(&bar->s_empty[buf], bph ^ 1);
           }
           __syncwarp();
-          TRACE(1, it, 0);
           tc_fence_after();
           if (elect_one()) {
-            issue_s_mma(tmem_u + buf * TILE, a_base, smem_u32(sm.slot(slot)), 0, nk);
+            issue_s_mma<TILE>(tmem_u + buf * TILE, a_base, smem_u32(sm.slot(slot)), 0, nk);
             tc_commit(&bar->empty[slot]);
             tc_commit(&bar->s_full[buf]);
           }
           __syncwarp();
-          TRACE(1, it, 1);
         }
         ++it;
       });
@@ -376,12 +664,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
       __syncwarp();
     }
   } else if (warp < kEpilogueWarps) {
-    // ------------------------------- epilogue -----------------------------------
     const int wg = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float c2 = p.inv_tau * kLog2e;
-    const uint64_t c2c2 = pack_f32x2(c2, c2), nc2nc2 = pack_f32x2(-c2, -c2);
     uint32_t it = 0;
     for (int64_t f = f0; f < f1;) {
       const int64_t I = f / p.CT, tb = f % p.CT;
@@ -393,79 +678,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const __grid_constant_
       const int li = row_ok ? p.labels[gi] : 0;
       const int4 rsig = p.sig[rb0 + I];
       float logD = 0.f;
-      if (PASS == 1 && row_ok) logD = p.inv_tau + logf(p.acc[gi].x);
-      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};       // PASS 0 fast path: packed partial row sums
-      float s0 = 0.f, s1 = 0.f;                          // PASS 0 slow: rowsum ; PASS 1: wl, wp
-      float cnt = 0.f, spx = 0.f;
+      if (row_ok) logD = p.inv_tau + logf(p.acc[gi].x);
+      float s0 = 0.f, s1 = 0.f;                          // wl, wp
 
-      for_each_tile<PASS>(p, rsig, tb, te, lane, [&](int64_t t) {
+      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t t) {
         const bool mine = static_cast<int>(it & 1) == wg;
         if (mine) {
           const int slot = it % p.nslot, buf = it % p.nbuf;
           const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
           const int64_t j0 = t * TILE;
-          bool slow = true;
-          if (PASS == 0) {
-            const bool diag = (j0 < gi0 + TILE) && (gi0 < j0 + TILE);
-            const bool tail = (j0 + TILE) > p.N;
-            slow = diag || tail || sig_overlap(rsig, p.sig[t]);
-          }
+          const int64_t dj = gi - j0;
+          const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+          const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
           mbar_wait(&bar->full[slot], ph);
           mbar_wait(&bar->s_full[buf], bph);
-          TRACE(2 + wg, it, 0);
           tc_fence_after();
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
           uint32_t va[32], vb[32];
-          if (p.dbg & 2) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) va[e] = vb[e] = 0;
-          }
-          if (!(p.dbg & 2)) {
           tmem_ld_32x32b_x32(taddr, va);
           tmem_wait_ld();
-          }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             uint32_t(&cur)[32] = (ch & 1) ? vb : va;
             uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch < 3 && !(p.dbg & 2)) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
-            if (PASS == 0) {
-              if (p.dbg & 1) { acc2[ch] ^= cur[ch]; }
-              else if (!slow) stats_chunk_fast(cur, c2c2, nc2nc2, acc2);
-              else stats_chunk_slow(cur, ch, j0, gi, p.N, li, lab_s, c2, s0, cnt, spx);
-            } else {
-              sp_chunk(cur, ch, j0, gi, p.N, li, lab_s, p, logD, s0, s1);
-            }
-            if (ch < 3 && !(p.dbg & 2)) tmem_wait_ld();
+            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
+            sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1);
+            if (ch < 3) tmem_wait_ld();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&bar->s_empty[buf]);
-            TRACE(2 + wg, it, 1);
             mbar_arrive(&bar->empty[slot]);
           }
         }
         ++it;
       });
 
-      if (row_ok) {
+      if (row_ok && s1 != 0.f) {
         float* a = reinterpret_cast<float*>(p.acc + gi);
-        if (PASS == 0) {
-          float lo, hi, rowsum = s0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            unpack_f32x2(acc2[k], lo, hi);
-            rowsum += lo + hi;
-          }
-          atomicAdd(a + 0, rowsum);
-          if (cnt != 0.f) atomicAdd(a + 1, cnt);
-          if (p.mode == SPCL_MODE_NONE && spx != 0.f) atomicAdd(a + 2, spx);
-        } else if (s1 != 0.f) {
-          atomicAdd(a + 2, s0);
-          atomicAdd(a + 3, s1);
-        }
+        atomicAdd(a + 2, s0);
+        atomicAdd(a + 3, s1);
       }
     }
   }
@@ -529,7 +783,7 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restr
 // =================================================================================================
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const SmemView sm = carve(smem_raw, p);
+  const SmemView sm = carve(smem_raw, p, TILE, true);
   Barriers* bar = sm.bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -545,145 +799,153 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
 
   int64_t f0, f1;
   cta_range(p, f0, f1);
-  const int64_t rb0 = p.row_begin / TILE;
+  const int64_t rb0 = p.row_begin / TILE, I0 = f0 / p.CT;
   const uint32_t tile_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES + META_BYTES;
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
-      uint32_t it = 0, seg = 0;
-      for (int64_t f = f0; f < f1; ++seg) {
-        const int64_t I = f / p.CT, tb = f % p.CT;
-        const int64_t te = min(p.CT, tb + (f1 - f));
-        f += te - tb;
-        const int32_t gi0 = static_cast<int32_t>(p.row_begin + I * TILE);
-        mbar_wait(&bar->a_empty, (seg & 1) ^ 1);
-        mbar_arrive_expect_tx(&bar->a_full, static_cast<uint32_t>(p.dc) * CHUNK_BYTES);
-        for (int c = 0; c < p.dc; ++c) tma_load_2d(sm.a_tile + c * CHUNK_BYTES, &tmap, &bar->a_full, c * 64, gi0);
-        for (int64_t t = tb; t < te; ++t) {
-          const int slot = it % p.nslot;
-          const uint32_t ph = (it / p.nslot) & 1;
-          mbar_wait(&bar->empty[slot], ph ^ 1);
-          TRACE(0, it, 0);
-          mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
-          uint8_t* dst = sm.slot(slot);
-          for (int c = 0; c < p.dc; ++c)
-            tma_load_2d(dst + c * CHUNK_BYTES, &tmap, &bar->full[slot], c * 64, static_cast<int32_t>(t * TILE));
-          bulk_load_1d(sm.slot_labels(slot), p.labels + t * TILE, META_LABEL_BYTES, &bar->full[slot]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            bulk_load_1d(sm.slot_stats(slot, k), p.row_stats + k * p.n_pad + t * TILE, TILE * 4, &bar->full[slot]);
-          ++it;
+      Ring rs(p.nslot);
+      for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next()) {
+        if (c.first()) {
+          const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
+          mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
+          mbar_arrive_expect_tx(&bar->a_full, static_cast<uint32_t>(p.dc) * CHUNK_BYTES);
+          for (int k = 0; k < p.dc; ++k) tma_load_2d(sm.a_tile + k * CHUNK_BYTES, &tmap, &bar->a_full, k * 64, gi0);
         }
+        const int slot = rs.idx;
+        mbar_wait(&bar->empty[slot], rs.ph ^ 1);
+        TRACE(0, c.it, 0);
+        mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
+        uint8_t* dst = sm.slot(slot);
+        for (int k = 0; k < p.dc; ++k)
+          tma_load_2d(dst + k * CHUNK_BYTES, &tmap, &bar->full[slot], k * 64, static_cast<int32_t>(c.t * TILE));
+        bulk_load_1d(sm.slot_labels(slot), p.labels + static_cast<int64_t>(c.t) * TILE, META_LABEL_BYTES, &bar->full[slot]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          bulk_load_1d(sm.slot_stats(slot, k), p.row_stats + k * p.n_pad + static_cast<int64_t>(c.t) * TILE, TILE * 4, &bar->full[slot]);
       }
     }
   } else if (warp == kMmaWarp0) {
-    // ---- S issuer: S(t) = Z_I Z_J^T into the next free S/T buffer; runs up to nbuf tiles ahead of T.Z ----
-    // (warp-uniform control flow; lane 0 polls, the elect.sync lane issues -- see fwd_kernel)
+    // ---- S issuer.  Pipe order:  S(0) .. S(nbuf-1),  then  T.Z(t), S(t + nbuf)  for every t.
+    // S(t) = Z_I Z_J^T into S/T buffer t % nbuf;  T.Z(t): dZ_I += T_IJ Z_J once the epilogue has written T(t)
+    // over S(t).  The two kinds are issued by two warps that hand the "turn" to each other when their last MMA
+    // has been issued (named barriers 1 / 2), so each warp's barrier round trips hide behind the other's
+    // blocking issue and the groups enter the pipe back to back in exactly that order (see stats_kernel).
+    // S(t + nbuf) overwrites the buffer T.Z(t) reads: the tensor pipe executes MMAs in issue order, so no round
+    // trip through an mbarrier is needed between the two (dbg bit 3 adds it for A/B checks); waiting for the
+    // commit instead would drain the pipe once per tile.
     const uint32_t a_base = smem_u32(sm.a_tile);
     const int nk = p.dc * 4;
-    uint32_t it = 0, seg = 0;
-    for (int64_t f = f0; f < f1; ++seg) {
-      const int64_t tb = f % p.CT;
-      const int64_t te = min(p.CT, tb + (f1 - f));
-      f += te - tb;
-      if (lane == 0) mbar_wait(&bar->a_full, seg & 1);
-      __syncwarp();
-      for (int64_t t = tb; t < te; ++t, ++it) {
-        const int slot = it % p.nslot, buf = it % p.nbuf;
-        const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
-        if (lane == 0) {
-          mbar_wait(&bar->full[slot], ph);
-          mbar_wait(&bar->s_empty[buf], bph ^ 1);
-        }
-        __syncwarp();
-        TRACE(1, it, 0);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_s_mma(tmem_u + sbuf0 + buf * TILE, a_base, smem_u32(sm.slot(slot)), 0, nk);
-          tc_commit(&bar->s_full[buf]);
-        }
-        __syncwarp();
-        TRACE(1, it, 1);
+    const bool safe = (p.dbg & 8) != 0;
+    const uint32_t nb = static_cast<uint32_t>(p.nbuf);
+    Ring ss(p.nslot), sb(p.nbuf);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ss.next(), sb.next()) {
+      if (lane == 0) {
+        if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
+        mbar_wait(&bar->full[ss.idx], ss.ph);
+        if (safe) mbar_wait(&bar->s_empty[sb.idx], sb.ph ^ 1);
       }
-      if (elect_one()) tc_commit(&bar->a_empty);      // only the S MMAs read the A tile
       __syncwarp();
+      if (c.it >= nb) named_bar_sync(1, 64);                  // T.Z(it - nbuf) has been issued
+      TRACE(1, c.it, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_s_mma<TILE>(tmem_u + sbuf0 + sb.idx * TILE, a_base, smem_u32(sm.slot(ss.idx)), 0, nk);
+        tc_commit(&bar->s_full[sb.idx]);
+        if (c.last()) tc_commit(&bar->a_empty);               // only the S MMAs read the A tile
+      }
+      __syncwarp();
+      if (c.it + 1 >= nb) named_bar_arrive(2, 64);            // T.Z(it + 1 - nbuf) may go
+      TRACE(1, c.it, 1);
     }
   } else if (warp == kMmaWarp1) {
-    // ---- T.Z issuer: dZ_I += T_IJ Z_J once the epilogue has written T(t) over S(t) ----
+    // ---- T.Z issuer
     const uint32_t idesc_tz = make_idesc_bf16(TILE, p.d_pad, false, true);
-    uint32_t it = 0, seg = 0;
-    for (int64_t f = f0; f < f1; ++seg) {
-      const int64_t tb = f % p.CT;
-      const int64_t te = min(p.CT, tb + (f1 - f));
-      f += te - tb;
-      for (int64_t t = tb; t < te; ++t, ++it) {
-        const int slot = it % p.nslot, buf = it % p.nbuf;
-        const uint32_t bph = (it / p.nbuf) & 1;
-        const bool first = (t == tb);
-        if (lane == 0) {
-          mbar_wait(&bar->t_full[buf], bph);
-          if (first) mbar_wait(&bar->dz_empty, (seg & 1) ^ 1);
-        }
-        __syncwarp();
-        TRACE(1, it, 2);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t b_base = smem_u32(sm.slot(slot));
-          const uint32_t a_tmem = tmem_u + sbuf0 + buf * TILE;
-#pragma unroll
-          for (int k = 0; k < TILE / 16; ++k) {
-            // B = Z_J read MN-major: the 64-wide MN (= d) atoms are the TMA panels (LBO = panel bytes),
-            // 8-row K (= j) groups are 1024 B apart (SBO); each K = 16 step advances 16 rows.
-            const uint64_t bd = make_smem_desc_sw128(b_base + k * 16 * 128, CHUNK_BYTES, 1024);
-            mma_ts(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && k == 0) ? 0u : 1u);
-          }
-          tc_commit(&bar->empty[slot]);
-          tc_commit(&bar->s_empty[buf]);
-        }
-        __syncwarp();
-        TRACE(1, it, 3);
+    const bool safe = (p.dbg & 8) != 0;
+    const uint32_t nb = static_cast<uint32_t>(p.nbuf);
+    Ring ts(p.nslot), tb(p.nbuf);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ts.next(), tb.next()) {
+      const bool first = c.first();
+      if (lane == 0) {
+        mbar_wait(&bar->t_full[tb.idx], tb.ph);
+        if (first) mbar_wait(&bar->dz_empty, (c.seg & 1) ^ 1);
       }
-      if (elect_one()) tc_commit(&bar->dz_full);
       __syncwarp();
+      if (c.it + nb - 1 < c.n) named_bar_sync(2, 64);         // S(it + nbuf - 1) has been issued
+      TRACE(1, c.it, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_base = smem_u32(sm.slot(ts.idx));
+        const uint32_t a_tmem = tmem_u + sbuf0 + tb.idx * TILE;
+#pragma unroll
+        for (int k = 0; k < TILE / 16; ++k) {
+          // B = Z_J read MN-major: the 64-wide MN (= d) atoms are the TMA panels (LBO = panel bytes),
+          // 8-row K (= j) groups are 1024 B apart (SBO); each K = 16 step advances 16 rows.
+          const uint64_t bd = make_smem_desc_sw128(b_base + k * 16 * 128, CHUNK_BYTES, 1024);
+          mma_ts(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && k == 0) ? 0u : 1u);
+        }
+        tc_commit(&bar->empty[ts.idx]);
+        if (safe) tc_commit(&bar->s_empty[tb.idx]);
+        if (c.last()) tc_commit(&bar->dz_full);
+      }
+      __syncwarp();
+      if (c.it + nb < c.n) named_bar_arrive(1, 64);           // S(it + nbuf) may go
+      TRACE(1, c.it, 3);
     }
   } else if (warp < kEpilogueWarps) {
     const int wg = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float c2 = p.inv_tau * kLog2e;
-    const uint64_t c2c2 = pack_f32x2(c2, c2), nc2nc2 = pack_f32x2(-c2, -c2);
+    const ExpK ek = make_expk<3>(p);
     const float coef = p.grad_out[0] * p.scalars[3] * p.inv_tau;
-    uint32_t it = 0, seg = 0;
-    for (int64_t f = f0; f < f1; ++seg) {
-      const int64_t I = f / p.CT, tb = f % p.CT;
-      const int64_t te = min(p.CT, tb + (f1 - f));
-      f += te - tb;
-      const int64_t gi0 = p.row_begin + I * TILE;
-      const int64_t gi = gi0 + r;
-      const bool row_ok = gi < p.row_end;
-      const int li = row_ok ? p.labels[gi] : 0;
-      const float logD_i = row_ok ? p.row_stats[gi] : 0.f;
-      const float invc_i = row_ok ? p.row_stats[p.n_pad + gi] : 0.f;
-      const float u_i = row_ok ? p.row_stats[3 * p.n_pad + gi] : 0.f;
-      const uint64_t uiui = pack_f32x2(u_i, u_i);
-      const int4 rsig = p.sig[rb0 + I];
+    int64_t gi0 = 0, gi = 0;
+    bool row_ok = false;
+    int li = 0;
+    float logD_i = 0.f, invc_i = 0.f, u_i = 0.f;
+    uint64_t uiui = 0ull;
+    int4 rsig = make_int4(0, 0, 0, 0);
 
-      for (int64_t t = tb; t < te; ++t, ++it) {
-        if (static_cast<int>(it & 1) != wg) continue;
-        const int slot = it % p.nslot, buf = it % p.nbuf;
-        const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
-        const int64_t j0 = t * TILE;
+    Ring rs(p.nslot), rbuf(p.nbuf);
+    auto tile_after = [&](uint32_t t) -> uint32_t {
+      uint32_t t2 = t + 2u;
+      while (t2 >= static_cast<uint32_t>(p.CT)) t2 -= static_cast<uint32_t>(p.CT);
+      return t2;
+    };
+    // signature of the next tile of this warpgroup, requested one tile ahead (see stats_kernel)
+    TileCursor c0(f0, f1, p.CT);
+    int4 nsig = p.sig[(c0.t + static_cast<uint32_t>(wg)) < static_cast<uint32_t>(p.CT) ? c0.t + wg : 0u];
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next(), rbuf.next()) {
+      if (c.first()) {
+        gi0 = p.row_begin + (I0 + c.seg) * TILE;
+        gi = gi0 + r;
+        row_ok = gi < p.row_end;
+        li = row_ok ? p.labels[gi] : 0;
+        logD_i = row_ok ? p.row_stats[gi] : 0.f;
+        invc_i = row_ok ? p.row_stats[p.n_pad + gi] : 0.f;
+        u_i = row_ok ? p.row_stats[3 * p.n_pad + gi] : 0.f;
+        uiui = pack_f32x2(u_i, u_i);
+        rsig = p.sig[rb0 + I0 + c.seg];
+      }
+      if (static_cast<int>(c.it & 1) == wg) {
+        const int slot = rs.idx, buf = rbuf.idx;
+        const uint32_t ph = rs.ph, bph = rbuf.ph;
+        const int64_t j0 = static_cast<int64_t>(c.t) * TILE;
+        const int4 csig = nsig;
+        nsig = p.sig[tile_after(c.t)];
         const bool diag = (j0 < gi0 + TILE) && (gi0 < j0 + TILE);
         const bool tail = (j0 + TILE) > p.N;
-        const bool slow = diag || tail || sig_overlap(rsig, p.sig[t]);
+        const bool slow = diag || tail || sig_overlap(rsig, csig);
         mbar_wait(&bar->full[slot], ph);
         mbar_wait(&bar->s_full[buf], bph);
-        TRACE(2 + wg, it, 0);
+        TRACE(2 + wg, c.it, 0);
         tc_fence_after();
         const int32_t* lab_s = sm.slot_labels(slot);
         const float* logD_s = sm.slot_stats(slot, 0);
         const float* invc_s = sm.slot_stats(slot, 1);
         const float* u_s = sm.slot_stats(slot, 3);
+        const int64_t dj = gi - j0;
+        const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+        const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
         const uint32_t taddr = lane_base + sbuf0 + buf * TILE;
         uint32_t va[32], vb[32];
         tmem_ld_32x32b_x32(taddr, va);
@@ -694,8 +956,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
           if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
           uint32_t pk[16];
-          if (!slow) bwd_chunk_fast(cur, u_s + ch * 32, c2c2, nc2nc2, uiui, pk);
-          else bwd_chunk_slow(cur, ch, j0, gi, p.N, li, lab_s, logD_s, invc_s, u_s, p, c2, logD_i, invc_i, u_i, pk);
+          if (!slow) {
+            bwd_chunk_fast(cur, u_s + ch * 32, ek, uiui, pk);
+          } else if (p.mode == SPCL_MODE_SOFT) {
+            bwd_chunk_slow<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          } else if (p.mode == SPCL_MODE_HARD) {
+            bwd_chunk_slow<SPCL_MODE_HARD>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          } else {
+            bwd_chunk_slow<SPCL_MODE_NONE>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          }
           if (ch < 3) tmem_wait_ld();
           // T (bf16) overwrites S columns [16 ch, 16 ch + 16), all of which were loaded before
           tmem_st_32x32b_x16(taddr + ch * 16, pk);
@@ -704,29 +976,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->t_full[buf]);
-        TRACE(2 + wg, it, 1);
+        TRACE(2 + wg, c.it, 1);
       }
 
-      // ---- drain dZ_I for this row-block segment: TMEM -> scale -> global accumulate ----
-      mbar_wait(&bar->dz_full, seg & 1);
-      tc_fence_after();
-      const int half = p.d_pad >> 1;
-      float* out = p.dz + (gi - p.row_begin) * p.lddz;
-      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_base + c0, v);
-        tmem_wait_ld();
-        if (row_ok) {
+      if (c.last()) {
+        // ---- drain dZ_I for this row-block segment: TMEM -> scale -> global accumulate ----
+        mbar_wait(&bar->dz_full, c.seg & 1);
+        tc_fence_after();
+        const int half = p.d_pad >> 1;
+        float* out = p.dz + (gi - p.row_begin) * p.lddz;
+        for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_base + c0, v);
+          tmem_wait_ld();
+          if (row_ok) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int col = c0 + e;
-            if (col < p.d) atomicAdd(out + col, __uint_as_float(v[e]) * coef);
+            for (int e = 0; e < 32; ++e) {
+              const int col = c0 + e;
+              if (col < p.d) atomicAdd(out + col, __uint_as_float(v[e]) * coef);
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->dz_empty);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar->dz_empty);
     }
   }
 
@@ -758,12 +1032,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_zb_tensor_map(CUtensorMap* map, const void* zb, int64_t n_pad, int d_pad) {
+// box = 64 columns (one 128-byte swizzle row) x box_rows anchors
+static int make_zb_tensor_map(CUtensorMap* map, const void* zb, int64_t n_pad, int d_pad, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return SPCL_ERR_NO_DRIVER;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(n_pad)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * 2};
-  const cuuint32_t box[2] = {64, TILE};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(zb), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -785,45 +1060,55 @@ static int num_sms() {
   return sms;
 }
 
-static int pick_slots(int dc) {
-  const size_t budget = 224 * 1024;   // of the 227 KB a CTA may own; 1 KB alignment slack on top
+static int pick_slots(int dc, int bn, bool meta) {
+  const size_t budget = 226 * 1024;   // of the 227 KB a CTA may own; includes the 1 KB alignment slack
   int nslot = kMaxSlots;
-  while (nslot > 2 && smem_payload_bytes(dc, nslot) + 1024 > budget) --nslot;
+  while (nslot > 1 && smem_payload_bytes(dc, nslot, bn, meta) + 1024 > budget) --nslot;
   return nslot;
 }
 
 static unsigned long long* g_trace = nullptr;
 static int g_dbg = 0;
 
+// minimax polynomials of 2^f on [-0.5, 0.5] (relative error 2.7e-6 / 7.5e-5)
+static const double kPoly4[5] = {0.999999261492568, 0.6931218184520522, 0.24024745066719647, 0.05591783074149139,
+                                 0.00957007737459198};
+static const double kPoly3[4] = {0.9999280966621894, 0.6932609900204585, 0.24261074551982187, 0.055171407593784125};
+
 static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad, const int32_t* labels,
                        const int32_t* sig, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
-                       int mode, bool bwd) {
+                       int mode) {
   if (n_total <= 0 || n_pad < n_total || n_pad % TILE != 0 || n_pad - n_total >= TILE) return SPCL_ERR_INVALID_ARG;
   if (d_pad <= 0 || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
   if (labels == nullptr || sig == nullptr) return SPCL_ERR_INVALID_ARG;
   if (row_begin < 0 || row_end > n_total || row_begin >= row_end) return SPCL_ERR_INVALID_ARG;
   if (row_begin % TILE != 0) return SPCL_ERR_UNSUPPORTED;
-  if (n_pad > (1LL << 31) - TILE) return SPCL_ERR_UNSUPPORTED;
+  if (n_pad > (1LL << 31) - 2 * TILE) return SPCL_ERR_UNSUPPORTED;
   if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_SOFT) return SPCL_ERR_INVALID_ARG;
   // exp(S - 1/tau) must stay a normal fp32 for S >= -1/tau
-  if (inv_tau > 43.f) return SPCL_ERR_UNSUPPORTED;
+  if (inv_tau > 40.f) return SPCL_ERR_UNSUPPORTED;   // also keeps the exponent splice of ex2_poly2 in range
   if (mode != SPCL_MODE_NONE && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
   p.N = n_total;
   p.n_pad = n_pad;
   p.row_begin = row_begin;
   p.row_end = row_end;
-  p.CT = n_pad / TILE;
+  p.CT128 = n_pad / TILE;
+  p.CT = p.CT128;
   p.RB = ceil_div(row_end - row_begin, TILE);
   p.d_pad = d_pad;
   p.dc = d_pad / 64;
-  p.nslot = pick_slots(p.dc);
-  p.nbuf = bwd ? min(3, (512 - d_pad) / TILE) : kMaxBufs;
   p.labels = labels;
   p.sig = reinterpret_cast<const int4*>(sig);
   p.inv_tau = inv_tau;
   p.gamma = gamma;
   p.inv_gamma = gamma > 0.f ? 1.f / gamma : 0.f;
   p.mode = mode;
+  p.c2 = inv_tau * kLog2e;
+  const float ci = floorf(p.c2);
+  const double scale = std::exp2(-(static_cast<double>(p.c2) - static_cast<double>(ci)));
+  p.ex_magic = 12582912.f - ci;
+  for (int i = 0; i < 5; ++i) p.pf[i] = static_cast<float>(kPoly4[i] * scale);
+  for (int i = 0; i < 4; ++i) p.pb[i] = static_cast<float>(kPoly3[i] * scale);
   p.trace = g_trace;
   p.dbg = g_dbg;
   return SPCL_OK;
@@ -833,6 +1118,11 @@ template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   SPCL_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
   return SPCL_OK;
+}
+
+static unsigned grid_for(const Params& p) {
+  const int64_t total = p.RB * p.CT;
+  return static_cast<unsigned>(total < num_sms() ? total : num_sms());
 }
 
 }  // namespace tc
@@ -845,29 +1135,52 @@ extern "C" int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_p
                                     float inv_tau, float gamma, int mode, float* acc, float* row_stats,
                                     float* partials, spcl_stream_t stream) {
   tc::Params p{};
-  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode, false);
+  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
   if (zb == nullptr || acc == nullptr || row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(zb) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15))
     return SPCL_ERR_INVALID_ARG;
   p.acc = reinterpret_cast<float4*>(acc);
-  CUtensorMap tmap;
-  rc = tc::make_zb_tensor_map(&tmap, zb, n_pad, d_pad);
-  if (rc != SPCL_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot) + 1024;
-  rc = tc::set_smem(tc::fwd_kernel<0>, smem);
-  if (rc != SPCL_OK) return rc;
-  rc = tc::set_smem(tc::fwd_kernel<1>, smem);
+  CUtensorMap tmap128;
+  rc = tc::make_zb_tensor_map(&tmap128, zb, n_pad, d_pad, tc::TILE);
   if (rc != SPCL_OK) return rc;
 
   SPCL_CUDA_TRY(cudaMemsetAsync(acc + row_begin * 4, 0, static_cast<size_t>(row_end - row_begin) * 16, s));
-  const int64_t total = p.RB * p.CT;
-  const unsigned grid = static_cast<unsigned>(total < tc::num_sms() ? total : tc::num_sms());
-  tc::fwd_kernel<0><<<grid, tc::NTHREADS, smem, s>>>(tmap, p);
+
+  // pass A: 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128
+  const bool wide = tc::pick_slots(p.dc, 256, false) >= 2 && !(tc::g_dbg & 16);
+  if (wide) {
+    tc::Params pa = p;
+    pa.CT = ceil_div(n_pad, 256);
+    pa.nslot = tc::pick_slots(p.dc, 256, false);
+    pa.nbuf = 2;
+    CUtensorMap tmap256;
+    rc = tc::make_zb_tensor_map(&tmap256, zb, n_pad, d_pad, 256);
+    if (rc != SPCL_OK) return rc;
+    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, 256, false) + 1024;
+    rc = tc::set_smem(tc::stats_kernel<256>, smem);
+    if (rc != SPCL_OK) return rc;
+    tc::stats_kernel<256><<<tc::grid_for(pa), tc::NTHREADS, smem, s>>>(tmap128, tmap256, pa);
+  } else {
+    tc::Params pa = p;
+    pa.nslot = tc::pick_slots(p.dc, 128, false);
+    pa.nbuf = 4;
+    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, 128, false) + 1024;
+    rc = tc::set_smem(tc::stats_kernel<128>, smem);
+    if (rc != SPCL_OK) return rc;
+    tc::stats_kernel<128><<<tc::grid_for(pa), tc::NTHREADS, smem, s>>>(tmap128, tmap128, pa);
+  }
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/stats");
+
   if (mode != SPCL_MODE_NONE) {
-    tc::fwd_kernel<1><<<grid, tc::NTHREADS, smem, s>>>(tmap, p);
+    tc::Params pb = p;
+    pb.nslot = tc::pick_slots(p.dc, 128, true);
+    pb.nbuf = tc::kMaxBufs;
+    const size_t smem = tc::smem_payload_bytes(pb.dc, pb.nslot, 128, true) + 1024;
+    rc = tc::set_smem(tc::sp_kernel, smem);
+    if (rc != SPCL_OK) return rc;
+    tc::sp_kernel<<<tc::grid_for(pb), tc::NTHREADS, smem, s>>>(tmap128, pb);
     SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/sp");
   }
   const unsigned fgrid = static_cast<unsigned>(ceil_div(row_end - row_begin, 256));
@@ -883,7 +1196,7 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
                                     int64_t row_end, float inv_tau, float gamma, int mode, float* dz,
                                     int64_t lddz, spcl_stream_t stream) {
   tc::Params p{};
-  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode, true);
+  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
   if (zb == nullptr || row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr)
     return SPCL_ERR_INVALID_ARG;
@@ -897,26 +1210,27 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
   p.grad_out = grad_out;
   p.dz = dz;
   p.lddz = lddz;
+  p.nslot = tc::pick_slots(p.dc, 128, true);
+  p.nbuf = (512 - d_pad) / tc::TILE < 3 ? (512 - d_pad) / tc::TILE : 3;
   CUtensorMap tmap;
-  rc = tc::make_zb_tensor_map(&tmap, zb, n_pad, d_pad);
+  rc = tc::make_zb_tensor_map(&tmap, zb, n_pad, d_pad, tc::TILE);
   if (rc != SPCL_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot) + 1024;
+  const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot, 128, true) + 1024;
   rc = tc::set_smem(tc::bwd_kernel, smem);
   if (rc != SPCL_OK) return rc;
   SPCL_CUDA_TRY(cudaMemsetAsync(dz, 0, static_cast<size_t>(row_end - row_begin) * lddz * sizeof(float), s));
-  const int64_t total = p.RB * p.CT;
-  const unsigned grid = static_cast<unsigned>(total < tc::num_sms() ? total : tc::num_sms());
-  tc::bwd_kernel<<<grid, tc::NTHREADS, smem, s>>>(tmap, p);
+  tc::bwd_kernel<<<tc::grid_for(p), tc::NTHREADS, smem, s>>>(tmap, p);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16");
   return SPCL_OK;
 }
 
-// debug only (not part of include/spcl.h): device buffer of 4 roles x 64 tiles x 4 events x u64, or NULL
+// debug only (not part of include/spcl.h)
 extern "C" int spcl_debug_set_flags(int flags) {
   tc::g_dbg = flags;
   return SPCL_OK;
 }
+// device buffer of 4 roles x 64 tiles x 4 events x u64, or NULL
 extern "C" int spcl_debug_set_trace(void* buf) {
   tc::g_trace = static_cast<unsigned long long*>(buf);
   return SPCL_OK;

@@ -1,7 +1,8 @@
 """Development tool: fwd_kernel<0> timeline summaries under the debug switches of supcon_tc.cu.
 
     python tools/gpu_exp.py [n] [d] [flags ...]
-flags: 1 = epilogue skips the math, 2 = epilogue skips tcgen05.ld, 4 = producer skips the TMA loads.
+flags: 1 = epilogue skips the math, 2 = epilogue skips tcgen05.ld, 4 = producer skips the TMA loads,
+       16 = 128 x 128 tiles in the stats kernel (default 128 x 256 when d <= 128).
 """
 import ctypes
 import pathlib
@@ -18,10 +19,10 @@ from spcl_b200 import ops  # noqa: E402
 from spcl_b200._native import lib  # noqa: E402
 
 
-def summary(name, tr, lo=8, hi=56):
+def summary(name, tr, lo=8, hi=56, both=True):
     t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
     idx = np.arange(lo, hi)
-    wg = 2 + (idx & 1)
+    wg = 2 + (0 if both else (idx & 1))
     prod = t[0, idx, 0]
     ready, issued = t[1, idx, 0], t[1, idx, 1]
     vis, done = t[wg, idx, 0], t[wg, idx, 1]
@@ -60,7 +61,7 @@ def main():
         ops.supcon_fwd(z1, z2, lab, None, 0.07, 8.0, 0, False, True)
         torch.cuda.synchronize()
         h.spcl_debug_set_trace(None)
-        summary(f"flags={f} fwd op {ms * 1e3:7.1f} us", tr)
+        summary(f"flags={f} fwd op {ms * 1e3:7.1f} us", tr, both=not (f & 16))
     h.spcl_debug_set_flags(0)
 
 

@@ -19,13 +19,13 @@ from spcl_b200._native import lib  # noqa: E402
 from spcl_b200.workloads import make_views  # noqa: E402
 
 
-def dump(name, tr, ntiles=24):
+def dump(name, tr, ntiles=24, both=False):
     t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
     base = t[t > 0].min()
     print(f"--- {name}: cycles relative to first stamp (CTA 0)")
     print("tile | prod.free | mma.ready mma.S_issued mma.T_ready mma.TZ_issued | epi.S_visible epi.done (wg)")
     for i in range(ntiles):
-        wg = 2 + (i & 1)
+        wg = 2 + (0 if both else (i & 1))
         r = lambda v: (int(v - base) if v > 0 else -1)
         print(f"{i:4d} | {r(t[0, i, 0]):9d} | {r(t[1, i, 0]):9d} {r(t[1, i, 1]):9d} {r(t[1, i, 2]):9d} {r(t[1, i, 3]):9d} |"
               f" {r(t[wg, i, 0]):9d} {r(t[wg, i, 1]):9d} ({'AB'[i & 1]})  epi_dur {int(t[wg, i, 1] - t[wg, i, 0])}")
@@ -50,7 +50,7 @@ def main():
     out = ops.supcon_fwd(z1, z2, lab, None, 0.07, 8.0, 0, False, True)      # mode NONE: only fwd_kernel<0> runs
     torch.cuda.synchronize()
     h.spcl_debug_set_trace(None)
-    dump("fwd_kernel<0>", tr)
+    dump("stats_kernel<256> (both warpgroups work on every tile; wg A shown)", tr, both=(d <= 128))
     scalars, row_stats, zpack, labels_full, sig = out
     gone = torch.ones(1, device="cuda")
     for _ in range(2):
