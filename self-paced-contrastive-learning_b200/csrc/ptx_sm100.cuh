@@ -77,6 +77,14 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
+// 16-byte read-only global load that stays where it is written (asm volatile): used to request data one loop
+// iteration ahead; a plain load was sunk by ptxas to just before its use and its L2 latency became exposed.
+__device__ __forceinline__ int4 ld_nc_v4_early(const int4* ptr) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
@@ -130,12 +138,26 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// SPCL_MBAR_SPIN = 1: poll with the non-blocking test_wait; 0: try_wait (the thread may be suspended for a
+// system-dependent time when the phase is not complete yet).
+#ifndef SPCL_MBAR_SPIN
+#define SPCL_MBAR_SPIN 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (true) {
     uint32_t ok;
+#if SPCL_MBAR_SPIN
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -143,8 +165,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#endif
     if (ok) return;
-    if ((++spins & 0xFF) == 0) {
+    if ((++spins & 0xFFF) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > SPCL_MBAR_TIMEOUT_NS) {
@@ -267,6 +290,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
+      : "memory");
+}
+// TMEM -> registers: this thread's lane, 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> TMEM: this thread's lane, 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      : : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
       : "memory");
 }
 // registers -> TMEM: this thread's lane, 16 consecutive 32-bit columns

@@ -1,2 +1,3 @@
-bash tools/gpu_round.sh v2c quick > gpurun_out/v2c_round.log 2>&1
-tail -12 gpurun_out/v2c_round.log | cut -c1-1000; tail -10 gpurun_out/v2c_trace.log
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+python tools/gpu_exp.py 16384 128 0
+python bench.py --steps 30 --warmup 5 --skip-cpu-baseline | cut -c1-1200

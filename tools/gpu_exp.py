@@ -26,15 +26,17 @@ def summary(name, tr, lo=8, hi=56, both=True):
     prod = t[0, idx, 0]
     ready, issued = t[1, idx, 0], t[1, idx, 1]
     vis, done = t[wg, idx, 0], t[wg, idx, 1]
+    visb, doneb = t[3, idx, 0], t[3, idx, 1]
     cad = (vis[-1] - vis[0]) / (len(idx) - 1)
     print(f"{name}: cadence {cad:7.0f} cyc/tile | prod->ready {np.mean(ready - prod):7.0f} | ready->issued "
-          f"{np.mean(issued - ready):6.0f} | issued->visible {np.mean(vis - issued):6.0f} | epi_dur {np.mean(done - vis):6.0f}")
+          f"{np.mean(issued - ready):6.0f} | issued->visible {np.mean(vis - issued):6.0f} | epi_dur {np.mean(done - vis):6.0f}"
+          + (f" | wg1 epi_dur {np.mean(doneb - visb):6.0f}" if both else ""))
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-    flags = [int(x) for x in sys.argv[3:]] or [0, 1, 2, 3, 4, 7]
+    flags = [int(x) for x in sys.argv[3:]] or [0, 1, 2, 3, 32, 33, 34, 35]
     g = torch.Generator().manual_seed(0)
     base = torch.randn(n, d, generator=g)
     z1 = torch.nn.functional.normalize(base + 0.7 * torch.randn(n, d, generator=g), dim=1).cuda()
@@ -61,7 +63,10 @@ def main():
         ops.supcon_fwd(z1, z2, lab, None, 0.07, 8.0, 0, False, True)
         torch.cuda.synchronize()
         h.spcl_debug_set_trace(None)
-        summary(f"flags={f} fwd op {ms * 1e3:7.1f} us", tr, both=not (f & 16))
+        if tr.any().item():
+            summary(f"flags={f} fwd op {ms * 1e3:7.1f} us", tr, both=not (f & 16))
+        else:
+            print(f"flags={f} fwd op {ms * 1e3:7.1f} us (library built without -DSPCL_TRACE=1: no timeline)")
     h.spcl_debug_set_flags(0)
 
 

@@ -50,7 +50,14 @@ def main():
     out = ops.supcon_fwd(z1, z2, lab, None, 0.07, 8.0, 0, False, True)      # mode NONE: only fwd_kernel<0> runs
     torch.cuda.synchronize()
     h.spcl_debug_set_trace(None)
-    dump("stats_kernel<256> (both warpgroups work on every tile; wg A shown)", tr, both=(d <= 128))
+    dump("stats_kernel<256> (both warpgroups work on every tile; wg A shown; T_ready = operands landed, TZ_issued = "
+         "S buffer free)", tr, both=(d <= 128))
+    t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
+    base = t[t > 0].min()
+    for w in (2, 3):
+        print(f"wg {w - 2}: tile: loop-top | S visible | first ld done | done")
+        for i in range(10, 20):
+            print(f"   {i}: {int(t[w, i, 3] - base)} | {int(t[w, i, 0] - base)} | {int(t[w, i, 2] - base)} | {int(t[w, i, 1] - base)}")
     scalars, row_stats, zpack, labels_full, sig = out
     gone = torch.ones(1, device="cuda")
     for _ in range(2):
