@@ -313,7 +313,7 @@ def main():
             "config": {"workload": workload, "anchors_N": N, "d": d, "rows_per_gpu": rows,
                        "hyper": {"tau": TAU, "gamma": GAMMA, "mode": MODE_NAME, "labels": spec["labels"]},
                        "l2": "256 MB flush between timed steps", "parallelism": f"row-shard x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 7 * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 6 * args.steps,
             "clocks": clocks, "loss": loss_val,
         }
         print(json.dumps(line), flush=True)

@@ -76,6 +76,15 @@ int spcl_l2norm_bwd(const void* gy, const void* y, const float* inv_norm, void* 
 int spcl_pack_views_bf16(const float* z1, const float* z2, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
                          void* dst, int64_t d_pad, spcl_stream_t stream);
 
+/* ---- fused operand preparation for the tensor-core path (one launch) ------------------------------
+ * zb (bf16 [n_pad][d_pad]) <- [z1 ; z2 ; 0], labels_full (int32 [n_pad]) <- [labels ; labels ; 0] (labels == NULL
+ * means the SimCLR identity target 0..n-1, contrast_loss3.py:140-143), sig <- block signatures of labels_full,
+ * partials[0..3) <- 0.  Equivalent to spcl_pack_views_bf16 + the label tiling of :163-165 + spcl_label_block_sig
+ * on zeroed buffers; replaces torch.cat (:26) and the list -> tensor label round trip (:135). */
+int spcl_supcon_prepare_bf16(const float* z1, const float* z2, int64_t n, int64_t d, int64_t ld1, int64_t ld2,
+                             const int32_t* labels, void* zb, int64_t n_pad, int64_t d_pad, int32_t* labels_full,
+                             int32_t* sig, float* partials, spcl_stream_t stream);
+
 /* per-128-anchor label signatures used to skip tiles without positives: int32[n_pad/128][4] */
 int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
                          spcl_stream_t stream);

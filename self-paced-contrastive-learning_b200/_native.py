@@ -29,6 +29,7 @@ SIGNATURES = {
     "spcl_l2norm_bwd": [_ptr, _ptr, _ptr, _ptr, _c.c_int, _i64, _i64, _i64, _ptr],
     "spcl_pack_views_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
     "spcl_label_block_sig": [_ptr, _i64, _i64, _ptr, _ptr],
+    "spcl_supcon_prepare_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr],
     "spcl_supcon_fwd_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
                              _ptr, _ptr],
     "spcl_supcon_bwd_bf16": [_ptr, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _f32,

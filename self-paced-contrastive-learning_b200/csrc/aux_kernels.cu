@@ -276,12 +276,96 @@ __global__ void __launch_bounds__(128) label_sig_kernel(const int32_t* __restric
   if (lane == 0) sig[blk] = make_int4(mn, mx, static_cast<int>(lo), static_cast<int>(hi));
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused operand preparation for the tensor-core path: one CTA per 128-anchor block
+//   zb[r][0..d_pad)  bf16 <- (r < n ? z1[r] : r < 2n ? z2[r-n] : 0), zero padded columns
+//   labels_full[r]        <- r < 2n ? (labels ? labels[r mod n] : r mod n) : 0
+//   sig[block]            <- {min, max, 64-bit bloom} of the block's labels (rows < 2n)
+//   partials[0..3)        <- 0
+// (replaces torch.cat :26, the list -> tensor label round trip :135 and four fill kernels; at cfg3 the eager
+// launch train in front of the first big kernel was ~8 % of the step)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                      int64_t n, int d, int64_t ld1, int64_t ld2, bool vec_ok,
+                                                      const int32_t* __restrict__ labels,
+                                                      __nv_bfloat16* __restrict__ zb, int d_pad,
+                                                      int32_t* __restrict__ labels_full, int4* __restrict__ sig,
+                                                      float* __restrict__ partials) {
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * SPCL_TILE;
+  const int64_t n_total = 2 * n;
+  const int groups = d_pad >> 3;
+  for (int g = threadIdx.x; g < SPCL_TILE * groups; g += blockDim.x) {
+    const int64_t r = row0 + g / groups;
+    const int c = (g % groups) << 3;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    if (r < n_total) {
+      const float* src = r < n ? z1 + r * ld1 : z2 + (r - n) * ld2;
+      if (vec_ok && c + 8 <= d) {
+        const float4 a = *reinterpret_cast<const float4*>(src + c);
+        const float4 b = *reinterpret_cast<const float4*>(src + c + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = (c + k) < d ? src[c + k] : 0.f;
+      }
+    }
+    Vec<__nv_bfloat162, 4> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<Vec<__nv_bfloat162, 4>*>(zb + r * d_pad + c) = o;
+  }
+  if (threadIdx.x < SPCL_TILE) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = row0 + threadIdx.x;
+    int mn = INT_MAX, mx = INT_MIN;
+    unsigned lo = 0u, hi = 0u;
+    int v = 0;
+    if (i < n_total) {
+      const int64_t h = i < n ? i : i - n;
+      v = labels != nullptr ? labels[h] : static_cast<int32_t>(h);
+      mn = mx = v;
+      const unsigned hsh = (static_cast<unsigned>(v) * 0x9E3779B1u) >> 26;
+      if (hsh < 32) lo = 1u << hsh; else hi = 1u << (hsh - 32);
+    }
+    labels_full[i] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+      hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    __shared__ int s_mn[4], s_mx[4];
+    __shared__ unsigned s_lo[4], s_hi[4];
+    if (lane == 0) {
+      s_mn[threadIdx.x >> 5] = mn;
+      s_mx[threadIdx.x >> 5] = mx;
+      s_lo[threadIdx.x >> 5] = lo;
+      s_hi[threadIdx.x >> 5] = hi;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        mn = min(mn, s_mn[k]);
+        mx = max(mx, s_mx[k]);
+        lo |= s_lo[k];
+        hi |= s_hi[k];
+      }
+      sig[blockIdx.x] = make_int4(mn, mx, static_cast<int>(lo), static_cast<int>(hi));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x >= 128 && threadIdx.x < 131) partials[threadIdx.x - 128] = 0.f;
+}
+
 }  // namespace aux
 }  // namespace spcl
 
 using namespace spcl;
 
-extern "C" int spcl_version(void) { return 100; }
+extern "C" int spcl_version(void) { return 101; }
 
 extern "C" const char* spcl_error_string(int code) {
   switch (code) {
@@ -333,6 +417,23 @@ extern "C" int spcl_pack_views_bf16(const float* z1, const float* z2, int64_t n,
   aux::pack_views_kernel<<<aux::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       z1, z2, n, (int)d, ld1, ld2, static_cast<__nv_bfloat16*>(dst), (int)d_pad, vec_ok);
   SPCL_LAUNCH_CHECK("spcl_pack_views_bf16");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_prepare_bf16(const float* z1, const float* z2, int64_t n, int64_t d, int64_t ld1,
+                                        int64_t ld2, const int32_t* labels, void* zb, int64_t n_pad, int64_t d_pad,
+                                        int32_t* labels_full, int32_t* sig, float* partials, spcl_stream_t stream) {
+  if (z1 == nullptr || z2 == nullptr || zb == nullptr || labels_full == nullptr || sig == nullptr ||
+      partials == nullptr || n <= 0 || d <= 0 || ld1 < d || ld2 < d)
+    return SPCL_ERR_INVALID_ARG;
+  if (d_pad < d || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
+  if (n_pad < 2 * n || n_pad % SPCL_TILE != 0 || n_pad - 2 * n >= SPCL_TILE) return SPCL_ERR_INVALID_ARG;
+  if (!aux::aligned16(zb) || !aux::aligned16(sig)) return SPCL_ERR_INVALID_ARG;
+  const bool vec_ok = aux::aligned16(z1) && aux::aligned16(z2) && ld1 % 4 == 0 && ld2 % 4 == 0;
+  aux::prepare_kernel<<<static_cast<unsigned>(n_pad / SPCL_TILE), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z1, z2, n, (int)d, ld1, ld2, vec_ok, labels, static_cast<__nv_bfloat16*>(zb), (int)d_pad, labels_full,
+      reinterpret_cast<int4*>(sig), partials);
+  SPCL_LAUNCH_CHECK("spcl_supcon_prepare_bf16");
   return SPCL_OK;
 }
 

@@ -112,30 +112,33 @@ def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[T
     n_pad = pad_to(N, nat.TILE)
     st = _stream(z1)
     inv_tau = 1.0 / float(temperature)
-    row_stats = torch.zeros(4, n_pad, dtype=torch.float32, device=dev)
-    partials = torch.zeros(3, dtype=torch.float32, device=dev)
     scalars = torch.empty(4, dtype=torch.float32, device=dev)
-
-    if labels is not None:
-        if labels.dtype != torch.int32 or labels.shape != (n,):
-            raise TypeError("labels must be int32[n]")
-        labels_full = torch.zeros(n_pad, dtype=torch.int32, device=dev)
-        labels_full[:n] = labels
-        labels_full[n:N] = labels
-    else:
-        labels_full = torch.empty(0, dtype=torch.int32, device=dev)
+    if labels is not None and (labels.dtype != torch.int32 or labels.shape != (n,)):
+        raise TypeError("labels must be int32[n]")
 
     if use_tc:
+        # one launch packs both views to bf16, tiles the labels, builds the block signatures and zeroes the
+        # partial sums; nothing on this path is initialised by a torch fill kernel
         d_pad = pad_to(d, 64)
-        zpack = torch.zeros(n_pad, d_pad, dtype=torch.bfloat16, device=dev)
-        nat.call("spcl_pack_views_bf16", _ptr(z1), _ptr(z2), n, d, z1.stride(0), z2.stride(0), _ptr(zpack),
-                 d_pad, st)
+        row_stats = torch.empty(4, n_pad, dtype=torch.float32, device=dev)
+        partials = torch.empty(3, dtype=torch.float32, device=dev)
+        zpack = torch.empty(n_pad, d_pad, dtype=torch.bfloat16, device=dev)
+        labels_full = torch.empty(n_pad, dtype=torch.int32, device=dev)
         sig = torch.empty(n_pad // nat.TILE, 4, dtype=torch.int32, device=dev)
-        nat.call("spcl_label_block_sig", _ptr(labels_full), N, n_pad, _ptr(sig), st)
         acc = torch.empty(n_pad, 4, dtype=torch.float32, device=dev)
+        nat.call("spcl_supcon_prepare_bf16", _ptr(z1), _ptr(z2), n, d, z1.stride(0), z2.stride(0), _ptr(labels),
+                 _ptr(zpack), n_pad, d_pad, _ptr(labels_full), _ptr(sig), _ptr(partials), st)
         nat.call("spcl_supcon_fwd_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), 0, N,
                  inv_tau, float(gamma), int(mode), _ptr(acc), _ptr(row_stats), _ptr(partials), st)
     else:
+        row_stats = torch.zeros(4, n_pad, dtype=torch.float32, device=dev)
+        partials = torch.zeros(3, dtype=torch.float32, device=dev)
+        if labels is not None:
+            labels_full = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+            labels_full[:n] = labels
+            labels_full[n:N] = labels
+        else:
+            labels_full = torch.empty(0, dtype=torch.int32, device=dev)
         zpack = torch.cat([z1, z2], dim=0)
         sig = torch.empty(0, 4, dtype=torch.int32, device=dev)
         nat.call("spcl_supcon_fwd_f32", _ptr(zpack), N, d, zpack.stride(0),
