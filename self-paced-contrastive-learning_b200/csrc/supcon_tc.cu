@@ -88,11 +88,15 @@ struct Params {
   int dbg;                     // debug experiment switches (tools/gpu_exp.py), normally 0
 };
 
-// debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0.
+// debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
+// (roles: 0 producer, 1 MMA issuers, 2 + w epilogue warp w).
 // Compiled in only with -DSPCL_TRACE=1 (tools/gpu_trace.py wants such a build): even the disabled checks cost
 // the single-thread roles and the epilogue a few dozen exposed cycles per tile.
 #ifndef SPCL_TRACE
 #define SPCL_TRACE 0
+#endif
+#ifndef SPCL_PAIR_DEFAULT
+#define SPCL_PAIR_DEFAULT 0
 #endif
 #if SPCL_TRACE
 #define TRACE(role, it_, ev)                                                                    \
@@ -186,6 +190,14 @@ struct Ring {
     }
   }
 };
+
+// One lane polls the mbarrier, the warp joins at __syncwarp: a probe by all 32 lanes is serialised in the
+// synchronisation unit and cost 150-350 cycles per wait in the epilogue warps (timeline: ~600-800 idle cycles
+// between two tiles of a warpgroup).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 
 // Calls f(t) for every column tile of [tb, te) the sp pass has to visit, in order, warp-uniformly: only
 // tiles whose label signature can match the row block's; 32 candidates are tested per step (one per lane)
@@ -531,8 +543,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
         const uint32_t jb = block_of(c.t);
         const int64_t j0 = static_cast<int64_t>(jb) * TILE;
         const bool inside = jb < ct128;
-        mbar_wait(&bar->s_full[buf], bph);
-        TRACE(2 + wg, c.it, 0);
+        mbar_wait_warp(&bar->s_full[buf], bph, lane);
+        TRACE(2 + warp, c.it, 0);
         tc_fence_after();
         if (inside && !(p.dbg & 2)) {
           const int64_t dj = gi - j0;
@@ -557,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->s_empty[buf]);
-        TRACE(2 + wg, c.it, 1);
+        TRACE(2 + warp, c.it, 1);
       }
       if (c.last()) {
         if (row_ok) {
@@ -700,8 +712,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const int64_t dj = gi - j0;
           const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
           const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
-          mbar_wait(&bar->full[slot], ph);
-          mbar_wait(&bar->s_full[buf], bph);
+          if (lane == 0) {
+            mbar_wait(&bar->full[slot], ph);
+            mbar_wait(&bar->s_full[buf], bph);
+          }
+          __syncwarp();
           tc_fence_after();
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
@@ -950,9 +965,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           mask = slow_mask(mask_grp);
         }
         const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
-        mbar_wait(&bar->full[slot], ph);
-        mbar_wait(&bar->s_full[buf], bph);
-        TRACE(2 + wg, c.it, 0);
+        if (lane == 0) {
+          mbar_wait(&bar->full[slot], ph);
+          mbar_wait(&bar->s_full[buf], bph);
+        }
+        __syncwarp();
+        TRACE(2 + warp, c.it, 0);
         tc_fence_after();
         const int32_t* lab_s = sm.slot_labels(slot);
         const float* logD_s = sm.slot_stats(slot, 0);
@@ -991,12 +1009,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->t_full[buf]);
-        TRACE(2 + wg, c.it, 1);
+        TRACE(2 + warp, c.it, 1);
       }
 
       if (c.last()) {
         // ---- drain dZ_I for this row-block segment: TMEM -> scale -> global accumulate ----
-        mbar_wait(&bar->dz_full, c.seg & 1);
+        mbar_wait_warp(&bar->dz_full, c.seg & 1, lane);
         tc_fence_after();
         const int half = p.d_pad >> 1;
         float* out = p.dz + (gi - p.row_begin) * p.lddz;
@@ -1024,6 +1042,312 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
   if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// backward on a CTA pair (cluster of 2, tcgen05 cta_group::2), d_pad = 128
+// =================================================================================================
+// The pair owns a "super row" of 256 anchors: CTA rank r works on row block 2 I2 + r, both walk the same column
+// tiles.  One M = 256 MMA per K step feeds both tensor cores; every CTA stages only HALF of each B operand, which
+// takes the shared-memory operand reads off the critical path (tools/mma_bench3.cu):
+//   S    : A = own Z_I (128 x 128, K-major), B = rows [64 r, 64 r + 64) of Z_J (K-major)          -> "Bs", 16 KB
+//   T.Z  : A = own T (TMEM),                 B = d columns [64 r, 64 r + 64) of all 128 rows of Z_J -> "Bt", 16 KB
+// Only the leader (rank 0) issues MMAs.  Barriers that gate an MMA (operands landed, T written, dZ drained) live
+// in the leader and collect the peer's TMA bytes / remote arrivals; barriers that an MMA releases (slot free, S
+// ready, dZ ready, A free) exist in both CTAs and are signalled by one multicast commit.
+struct Barriers2 {
+  uint64_t full[kMaxSlots];      // leader: Bs + Bt of both CTAs landed
+  uint64_t mfull[kMaxSlots];     // local: labels + column statistics landed
+  uint64_t empty[kMaxSlots];     // local: T.Z of the tile in this slot has completed
+  uint64_t s_full[kMaxBufs];     // local: S tile complete
+  uint64_t t_full[kMaxBufs];     // leader: T written by the epilogue warps of both CTAs (8 arrivals)
+  uint64_t a_full, a_empty, dz_full, dz_empty;
+  uint32_t tmem_base;
+};
+
+constexpr int kPairSlotBytes = 32768;          // Bs 16 KB + Bt 16 KB
+constexpr int kPairATileBytes = 32768;
+
+__host__ __device__ inline size_t pair_smem_bytes(int nslot) {
+  return static_cast<size_t>(kPairATileBytes) + static_cast<size_t>(nslot) * (kPairSlotBytes + META_BYTES) +
+         sizeof(Barriers2);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+    bwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_tile = base;
+  uint8_t* slots = base + kPairATileBytes;
+  uint8_t* meta = slots + static_cast<size_t>(p.nslot) * kPairSlotBytes;
+  Barriers2* bar = reinterpret_cast<Barriers2*>(meta + static_cast<size_t>(p.nslot) * META_BYTES);
+  auto slot_ptr = [&](int s_) -> uint8_t* { return slots + static_cast<size_t>(s_) * kPairSlotBytes; };
+  auto slot_labels = [&](int s_) -> int32_t* { return reinterpret_cast<int32_t*>(meta + static_cast<size_t>(s_) * META_BYTES); };
+  auto slot_stats = [&](int s_, int k) -> float* {
+    return reinterpret_cast<float*>(meta + static_cast<size_t>(s_) * META_BYTES + META_LABEL_BYTES) + k * TILE;
+  };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == kMmaWarp0 && lane == 0) {
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&bar->full[i], 1);
+      mbar_init(&bar->mfull[i], 1);
+      mbar_init(&bar->empty[i], 1);
+    }
+    for (int i = 0; i < kMaxBufs; ++i) {
+      mbar_init(&bar->s_full[i], 1);
+      mbar_init(&bar->t_full[i], 8);
+    }
+    mbar_init(&bar->a_full, 1);
+    mbar_init(&bar->a_empty, 1);
+    mbar_init(&bar->dz_full, 1);
+    mbar_init(&bar->dz_empty, 16);
+    fence_mbar_init();
+  }
+  if (warp == kAllocWarp) tmem_alloc_pair<kTmemCols>(&bar->tmem_base);
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer's barriers are initialised before anything targets them
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_base;
+  const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
+  const uint32_t sbuf0 = static_cast<uint32_t>(TILE);       // TMEM columns [0, 128) hold dZ
+
+  // flattened (super row, column tile) range of this PAIR
+  int64_t f0, f1;
+  {
+    const int64_t total = p.RB * p.CT, nc = gridDim.x >> 1, c = blockIdx.x >> 1;     // p.RB = super rows here
+    f0 = total * c / nc;
+    f1 = total * (c + 1) / nc;
+  }
+  const int64_t rb0 = p.row_begin / TILE, I0 = f0 / p.CT;
+  auto row_block = [&](uint32_t seg) -> int64_t { return 2 * (I0 + seg) + rank; };   // relative to row_begin
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const uint32_t a_full_l = mapa_u32(smem_u32(&bar->a_full), 0);
+      Ring rs(p.nslot);
+      for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next()) {
+        if (c.first()) {
+          const int32_t gi0 = static_cast<int32_t>(p.row_begin + row_block(c.seg) * TILE);
+          mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&bar->a_full, 2u * kPairATileBytes);
+          for (int k = 0; k < 2; ++k) tma_load_2d_pair(a_tile + k * CHUNK_BYTES, &tmap_a, a_full_l, k * 64, gi0);
+        }
+        const int slot = rs.idx;
+        mbar_wait(&bar->empty[slot], rs.ph ^ 1);
+        TRACE(0, c.it, 0);
+        const uint32_t full_l = mapa_u32(smem_u32(&bar->full[slot]), 0);
+        if (rank == 0) mbar_arrive_expect_tx(&bar->full[slot], 2u * kPairSlotBytes);
+        uint8_t* dst = slot_ptr(slot);
+        const int32_t j0 = static_cast<int32_t>(c.t * TILE);
+        // Bs: my 64 rows of Z_J, both 64-column panels (K-major B of the S GEMM)
+        for (int k = 0; k < 2; ++k)
+          tma_load_2d_pair(dst + k * 8192, &tmap_b, full_l, k * 64, j0 + 64 * static_cast<int32_t>(rank));
+        // Bt: my 64-column panel of all 128 rows of Z_J (MN-major B of the T.Z GEMM)
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d_pair(dst + 16384 + h * 8192, &tmap_b, full_l, 64 * static_cast<int32_t>(rank), j0 + 64 * h);
+        mbar_arrive_expect_tx(&bar->mfull[slot], META_BYTES);
+        bulk_load_1d(slot_labels(slot), p.labels + static_cast<int64_t>(c.t) * TILE, META_LABEL_BYTES, &bar->mfull[slot]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          bulk_load_1d(slot_stats(slot, k), p.row_stats + k * p.n_pad + static_cast<int64_t>(c.t) * TILE, TILE * 4,
+                       &bar->mfull[slot]);
+      }
+    }
+  } else if (warp == kMmaWarp0 && rank == 0) {
+    // ---- S issuer (see bwd_kernel for the issue order and the turn handoff with the T.Z issuer)
+    constexpr uint32_t idesc_s = make_idesc_bf16(2 * TILE, TILE, false, false);
+    const uint32_t a_base = smem_u32(a_tile);
+    const uint32_t nb = static_cast<uint32_t>(p.nbuf);
+    Ring ss(p.nslot), sb(p.nbuf);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ss.next(), sb.next()) {
+      if (lane == 0) {
+        if (c.first()) mbar_wait_cluster(&bar->a_full, c.seg & 1);
+        mbar_wait_cluster(&bar->full[ss.idx], ss.ph);
+      }
+      __syncwarp();
+      if (c.it >= nb) named_bar_sync(1, 64);                  // T.Z(it - nbuf) has been issued
+      TRACE(1, c.it, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_base = smem_u32(slot_ptr(ss.idx));
+        const uint32_t d_tmem = tmem_u + sbuf0 + sb.idx * TILE;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
+          const uint32_t pb = static_cast<uint32_t>(kk >> 2) * 8192 + static_cast<uint32_t>(kk & 3) * 32;
+          mma_ss_pair(d_tmem, make_smem_desc_sw128(a_base + pa, 16, 1024), make_smem_desc_sw128(b_base + pb, 16, 1024),
+                      idesc_s, kk != 0 ? 1u : 0u);
+        }
+        tc_commit_pair(&bar->s_full[sb.idx]);
+        if (c.last()) tc_commit_pair(&bar->a_empty);
+      }
+      __syncwarp();
+      if (c.it + 1 >= nb) named_bar_arrive(2, 64);            // T.Z(it + 1 - nbuf) may go
+      TRACE(1, c.it, 1);
+    }
+  } else if (warp == kMmaWarp1 && rank == 0) {
+    // ---- T.Z issuer
+    constexpr uint32_t idesc_tz = make_idesc_bf16(2 * TILE, TILE, false, true);
+    const uint32_t nb = static_cast<uint32_t>(p.nbuf);
+    Ring ts(p.nslot), tb(p.nbuf);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ts.next(), tb.next()) {
+      const bool first = c.first();
+      if (lane == 0) {
+        mbar_wait_cluster(&bar->t_full[tb.idx], tb.ph);
+        if (first) mbar_wait_cluster(&bar->dz_empty, (c.seg & 1) ^ 1);
+      }
+      __syncwarp();
+      if (c.it + nb - 1 < c.n) named_bar_sync(2, 64);         // S(it + nbuf - 1) has been issued
+      TRACE(1, c.it, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_base = smem_u32(slot_ptr(ts.idx)) + 16384;
+        const uint32_t a_tmem = tmem_u + sbuf0 + tb.idx * TILE;
+#pragma unroll
+        for (int k = 0; k < TILE / 16; ++k) {
+          const uint64_t bd = make_smem_desc_sw128(b_base + k * 16 * 128, CHUNK_BYTES, 1024);
+          mma_ts_pair(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && k == 0) ? 0u : 1u);
+        }
+        tc_commit_pair(&bar->empty[ts.idx]);
+        if (c.last()) tc_commit_pair(&bar->dz_full);
+      }
+      __syncwarp();
+      if (c.it + nb < c.n) named_bar_arrive(1, 64);           // S(it + nbuf) may go
+      TRACE(1, c.it, 3);
+    }
+  } else if (warp < kEpilogueWarps) {
+    const int wg = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const ExpK ek = make_expk<3>(p);
+    const float coef = p.grad_out[0] * p.scalars[3] * p.inv_tau;
+    int64_t gi0 = 0, gi = 0;
+    bool row_ok = false;
+    int li = 0;
+    float logD_i = 0.f, invc_i = 0.f, u_i = 0.f;
+    uint64_t uiui = 0ull;
+    int4 rsig = make_int4(0, 0, 0, 0);
+
+    Ring rs(p.nslot), rbuf(p.nbuf);
+    const uint32_t ct128 = static_cast<uint32_t>(p.CT128);
+    const uint32_t tail_jb = (p.N % TILE) ? ct128 - 1u : 0xffffffffu;
+    uint32_t row_jb = 0;
+    auto slow_mask = [&](uint32_t grp) -> uint32_t {
+      const uint32_t t = (grp << 5) + static_cast<uint32_t>(lane);
+      bool slow = true;
+      if (t < ct128) slow = t == row_jb || t == tail_jb || sig_overlap(rsig, p.sig[t]);
+      return __ballot_sync(kFullMask, slow);
+    };
+    uint32_t mask = 0, mask_grp = 0xffffffffu;
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next(), rbuf.next()) {
+      if (c.first()) {
+        gi0 = p.row_begin + row_block(c.seg) * TILE;
+        gi = gi0 + r;
+        row_jb = static_cast<uint32_t>(gi0 / TILE);
+        row_ok = gi < p.row_end;
+        li = row_ok ? p.labels[gi] : 0;
+        logD_i = row_ok ? p.row_stats[gi] : 0.f;
+        invc_i = row_ok ? p.row_stats[p.n_pad + gi] : 0.f;
+        u_i = row_ok ? p.row_stats[3 * p.n_pad + gi] : 0.f;
+        uiui = pack_f32x2(u_i, u_i);
+        rsig = p.sig[rb0 + row_block(c.seg)];
+        mask_grp = 0xffffffffu;
+      }
+      if (static_cast<int>(c.it & 1) == wg) {
+        const int slot = rs.idx, buf = rbuf.idx;
+        const uint32_t ph = rs.ph, bph = rbuf.ph;
+        const int64_t j0 = static_cast<int64_t>(c.t) * TILE;
+        if ((c.t >> 5) != mask_grp) {
+          mask_grp = c.t >> 5;
+          mask = slow_mask(mask_grp);
+        }
+        const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
+        TRACE(2 + warp, c.it, 3);
+        if (lane == 0) {
+          mbar_wait(&bar->mfull[slot], ph);
+          mbar_wait(&bar->s_full[buf], bph);
+        }
+        __syncwarp();
+        TRACE(2 + warp, c.it, 0);
+        tc_fence_after();
+        const int32_t* lab_s = slot_labels(slot);
+        const float* logD_s = slot_stats(slot, 0);
+        const float* invc_s = slot_stats(slot, 1);
+        const float* u_s = slot_stats(slot, 3);
+        const int64_t dj = gi - j0;
+        const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+        const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
+        const uint32_t taddr = lane_base + sbuf0 + buf * TILE;
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(taddr, va);
+        tmem_wait_ld();
+        TRACE(2 + warp, c.it, 2);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+          if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
+          uint32_t pk[16];
+          if (!slow) {
+            bwd_chunk_fast(cur, u_s + ch * 32, ek, uiui, pk);
+          } else if (p.mode == SPCL_MODE_SOFT) {
+            bwd_chunk_slow<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          } else if (p.mode == SPCL_MODE_HARD) {
+            bwd_chunk_slow<SPCL_MODE_HARD>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          } else {
+            bwd_chunk_slow<SPCL_MODE_NONE>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
+                                           u_i, pk);
+          }
+          if (ch < 3) tmem_wait_ld();
+          tmem_st_32x32b_x16(taddr + ch * 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar->t_full[buf]), 0));
+        TRACE(2 + warp, c.it, 1);
+      }
+
+      if (c.last()) {
+        // ---- drain this CTA's dZ rows: TMEM -> scale -> global accumulate ----
+        mbar_wait_warp(&bar->dz_full, c.seg & 1, lane);
+        tc_fence_after();
+        float* out = p.dz + (gi - p.row_begin) * p.lddz;
+        for (int c0 = wg * 64; c0 < (wg + 1) * 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_base + c0, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int col = c0 + e;
+              if (col < p.d) atomicAdd(out + col, __uint_as_float(v[e]) * coef);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar->dz_empty), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // no MMA, multicast commit or remote arrive is still in flight
+  if (warp == kAllocWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 
@@ -1085,6 +1409,18 @@ static int pick_slots(int dc, int bn, bool meta) {
 static unsigned long long* g_trace = nullptr;
 static int g_dbg = 0;
 
+// how many 2-CTA clusters of the pair kernels can be resident at once (GPCs with an odd SM count lose one SM)
+static int max_pair_clusters(size_t smem_bytes);
+// SPCL_PAIR=0/1 overrides the default (development A/B switch); debug flag 32 forces the single-CTA kernels
+static bool pair_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("SPCL_PAIR");
+    env = (e == nullptr) ? SPCL_PAIR_DEFAULT : (e[0] != '0');
+  }
+  return env != 0 && !(g_dbg & 32);
+}
+
 // minimax polynomials of 2^f on [-0.5, 0.5] (relative error 2.7e-6 / 7.5e-5)
 static const double kPoly4[5] = {0.999999261492568, 0.6931218184520522, 0.24024745066719647, 0.05591783074149139,
                                  0.00957007737459198};
@@ -1138,6 +1474,30 @@ static int set_smem(K kernel, size_t bytes) {
 static unsigned grid_for(const Params& p) {
   const int64_t total = p.RB * p.CT;
   return static_cast<unsigned>(total < num_sms() ? total : num_sms());
+}
+
+static int max_pair_clusters(size_t smem_bytes) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, bwd2_kernel, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    n = 0;
+  }
+  cached = n;
+  if (std::getenv("SPCL_DEBUG") != nullptr) fprintf(stderr, "spcl: %d resident CTA pairs (%d SMs)\n", n, num_sms());
+  return cached;
 }
 
 }  // namespace tc
@@ -1231,6 +1591,29 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
   rc = tc::make_zb_tensor_map(&tmap, zb, n_pad, d_pad, tc::TILE);
   if (rc != SPCL_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  // CTA-pair kernel: d_pad = 128 and an even number of row blocks (debug flag 32 forces the single-CTA kernel)
+  if (d_pad == 128 && p.RB % 2 == 0 && tc::pair_enabled()) {
+    CUtensorMap tmap64;
+    rc = tc::make_zb_tensor_map(&tmap64, zb, n_pad, d_pad, 64);
+    if (rc != SPCL_OK) return rc;
+    tc::Params q = p;
+    q.RB = p.RB / 2;                      // super rows of 256 anchors
+    q.nslot = 5;
+    q.nbuf = 3;
+    const size_t smem2 = tc::pair_smem_bytes(q.nslot) + 1024;
+    rc = tc::set_smem(tc::bwd2_kernel, smem2);
+    if (rc != SPCL_OK) return rc;
+    const int64_t total = q.RB * q.CT;
+    const int maxc = tc::max_pair_clusters(smem2);
+    if (maxc > 0) {
+      const unsigned nclusters = static_cast<unsigned>(total < maxc ? total : maxc);
+      SPCL_CUDA_TRY(cudaMemsetAsync(dz, 0, static_cast<size_t>(row_end - row_begin) * lddz * sizeof(float), s));
+      tc::bwd2_kernel<<<2 * nclusters, tc::NTHREADS, smem2, s>>>(tmap, tmap64, q);
+      SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16/pair");
+      return SPCL_OK;
+    }
+  }
   const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot, 128, true) + 1024;
   rc = tc::set_smem(tc::bwd_kernel, smem);
   if (rc != SPCL_OK) return rc;
@@ -1245,7 +1628,7 @@ extern "C" int spcl_debug_set_flags(int flags) {
   tc::g_dbg = flags;
   return SPCL_OK;
 }
-// device buffer of 4 roles x 64 tiles x 4 events x u64, or NULL
+// device buffer of 10 roles x 64 tiles x 4 events x u64, or NULL
 extern "C" int spcl_debug_set_trace(void* buf) {
   tc::g_trace = static_cast<unsigned long long*>(buf);
   return SPCL_OK;

@@ -20,13 +20,13 @@ from spcl_b200._native import lib  # noqa: E402
 
 
 def summary(name, tr, lo=8, hi=56, both=True):
-    t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
+    t = tr.view(10, 64, 4).cpu().numpy().astype("int64")
     idx = np.arange(lo, hi)
-    wg = 2 + (0 if both else (idx & 1))
+    wg = 2 + (0 if both else 4 * (idx & 1))
     prod = t[0, idx, 0]
     ready, issued = t[1, idx, 0], t[1, idx, 1]
     vis, done = t[wg, idx, 0], t[wg, idx, 1]
-    visb, doneb = t[3, idx, 0], t[3, idx, 1]
+    visb, doneb = t[6, idx, 0], t[6, idx, 1]
     cad = (vis[-1] - vis[0]) / (len(idx) - 1)
     print(f"{name}: cadence {cad:7.0f} cyc/tile | prod->ready {np.mean(ready - prod):7.0f} | ready->issued "
           f"{np.mean(issued - ready):6.0f} | issued->visible {np.mean(vis - issued):6.0f} | epi_dur {np.mean(done - vis):6.0f}"
@@ -45,7 +45,7 @@ def main():
     h = lib()
     h.spcl_debug_set_trace.argtypes = [ctypes.c_void_p]
     h.spcl_debug_set_flags.argtypes = [ctypes.c_int]
-    tr = torch.zeros(4 * 64 * 4, dtype=torch.int64, device="cuda")
+    tr = torch.zeros(10 * 64 * 4, dtype=torch.int64, device="cuda")
     for f in flags:
         h.spcl_debug_set_flags(f)
         for _ in range(2):

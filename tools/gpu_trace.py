@@ -20,15 +20,21 @@ from spcl_b200.workloads import make_views  # noqa: E402
 
 
 def dump(name, tr, ntiles=24, both=False):
-    t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
+    t = tr.view(10, 64, 4).cpu().numpy().astype("int64")
     base = t[t > 0].min()
+    r = lambda v: (int(v - base) if v > 0 else -1)
     print(f"--- {name}: cycles relative to first stamp (CTA 0)")
-    print("tile | prod.free | mma.ready mma.S_issued mma.T_ready mma.TZ_issued | epi.S_visible epi.done (wg)")
+    print("tile | prod.free | mma.ready mma.S_issued mma.T_ready mma.TZ_issued | per epilogue warp of the owning warpgroup: "
+          "loop-top/S-visible/first-ld/done")
     for i in range(ntiles):
-        wg = 2 + (0 if both else (i & 1))
-        r = lambda v: (int(v - base) if v > 0 else -1)
-        print(f"{i:4d} | {r(t[0, i, 0]):9d} | {r(t[1, i, 0]):9d} {r(t[1, i, 1]):9d} {r(t[1, i, 2]):9d} {r(t[1, i, 3]):9d} |"
-              f" {r(t[wg, i, 0]):9d} {r(t[wg, i, 1]):9d} ({'AB'[i & 1]})  epi_dur {int(t[wg, i, 1] - t[wg, i, 0])}")
+        wgs = (0, 1) if both else (i & 1,)
+        per = []
+        for wg in wgs:
+            for q in range(4):
+                w = 2 + wg * 4 + q
+                per.append(f"w{wg * 4 + q}: {r(t[w, i, 3])}/{r(t[w, i, 0])}/{r(t[w, i, 2])}/{r(t[w, i, 1])}")
+        print(f"{i:4d} | {r(t[0, i, 0]):9d} | {r(t[1, i, 0]):9d} {r(t[1, i, 1]):9d} {r(t[1, i, 2]):9d} {r(t[1, i, 3]):9d} | "
+              + "  ".join(per))
 
 
 def main():
@@ -42,7 +48,7 @@ def main():
     lab = labels.int().cuda()
     h = lib()
     h.spcl_debug_set_trace.argtypes = [ctypes.c_void_p]
-    tr = torch.zeros(4 * 64 * 4, dtype=torch.int64, device="cuda")
+    tr = torch.zeros(10 * 64 * 4, dtype=torch.int64, device="cuda")
     for _ in range(2):
         out = ops.supcon_fwd(z1, z2, lab, None, 0.07, 8.0, 0, False, True)
     torch.cuda.synchronize()
@@ -52,12 +58,6 @@ def main():
     h.spcl_debug_set_trace(None)
     dump("stats_kernel<256> (both warpgroups work on every tile; wg A shown; T_ready = operands landed, TZ_issued = "
          "S buffer free)", tr, both=(d <= 128))
-    t = tr.view(4, 64, 4).cpu().numpy().astype("int64")
-    base = t[t > 0].min()
-    for w in (2, 3):
-        print(f"wg {w - 2}: tile: loop-top | S visible | first ld done | done")
-        for i in range(10, 20):
-            print(f"   {i}: {int(t[w, i, 3] - base)} | {int(t[w, i, 0] - base)} | {int(t[w, i, 2] - base)} | {int(t[w, i, 1] - base)}")
     scalars, row_stats, zpack, labels_full, sig = out
     gone = torch.ones(1, device="cuda")
     for _ in range(2):
