@@ -17,7 +17,10 @@
  *     (reference: torch.eq on the target, contrast_loss3.py:136, tiled 2x2, diagonal removed :163-167).
  *   - tri-state mask (fp32 path only): uint8[n_half*n_half], 1 = positive, 0 = negative,
  *     anything else = ignored (reference: mask == 1 / mask == 0, :130-131).
- *   - mode: SPCL_MODE_NONE = SupConLoss1 (W == 1), HARD / SOFT = SelfPacedSupConLoss._self_paced_mask :207-214.
+ *   - mode: SPCL_MODE_NONE = SupConLoss1 (W == 1), HARD / SOFT = SelfPacedSupConLoss._self_paced_mask :207-214,
+ *     EXCL = SupConLoss1(exclude_other_pos=True) :97-100 (fp32 path only; the bf16 entry points return
+ *     SPCL_ERR_UNSUPPORTED).  In EXCL mode row_stats plane 0 holds B_i = negsum_i / (neg_ratio_i + 1e-4) in
+ *     units of exp(-1/tau), plane 2 is 1 and plane 3 is v_i = (1/c_i) sum_{j in P_i} 1 / (E_ij + B_i) / (neg_ratio_i + 1e-4).
  *   - row sharding: a call owns anchor rows [row_begin, row_end) against all N columns.
  *   - row_stats: four planes of `stride` floats each (stride = n_pad on the tensor-core path):
  *     plane 0 logD_i (natural-log row logsumexp over valid columns), plane 1 1/c_i (c_i = positive
@@ -45,6 +48,7 @@ extern "C" {
 #define SPCL_MODE_NONE 0
 #define SPCL_MODE_HARD 1
 #define SPCL_MODE_SOFT 2
+#define SPCL_MODE_EXCL 3  /* SupConLoss1(exclude_other_pos=True), contrast_loss3.py:97-100; fp32 path only */
 
 #define SPCL_DTYPE_F32 0
 #define SPCL_DTYPE_BF16 1

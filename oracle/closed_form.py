@@ -102,7 +102,8 @@ def supcon_closed_form(z1, z2, *, target=None, mask=None, temperature: float = 0
                        row_range=None, anchor_labels=None) -> dict:
     """Loss, ratio and gradient in fp64.
 
-    ``mode``: "none" (SupConLoss1), "hard", anything else = soft.
+    ``mode``: "none" (SupConLoss1), "excl" (SupConLoss1 with ``exclude_other_pos=True``, :97-100),
+    "hard", anything else = soft.
     ``row_range``: optional (r0, r1) -- only these anchor rows contribute to the
     *partial* sums returned under ``partial`` (used by the row-sharding tests);
     ``loss``/``ratio`` are always the full-problem values.
@@ -130,6 +131,9 @@ def supcon_closed_form(z1, z2, *, target=None, mask=None, temperature: float = 0
         masks = _Masks(n, codes=codes_from_target(target))
     else:
         masks = _Masks(n, codes=np.arange(n, dtype=np.int64))  # SimCLR (:140-143)
+
+    if mode == "excl":
+        return _excl_closed_form(Z, n, masks, inv_tau, block, grad_out, want_grad)
 
     logD = np.empty(N)
     c = np.empty(N)
@@ -194,6 +198,63 @@ def supcon_closed_form(z1, z2, *, target=None, mask=None, temperature: float = 0
                          - np.where(valid, A[i0:i1, None] * np.exp(llh_r), 0.0))
             dS_c = -k * (np.where(posT, W_c / c[None, :], 0.0)
                          - np.where(validT, A[None, :] * np.exp(llh_c), 0.0))
+        dZ[i0:i1] = ((dS_r + dS_c) @ Z) * inv_tau
+    out["dz1"] = dZ[:n]
+    out["dz2"] = dZ[n:]
+    return out
+
+
+def _excl_closed_form(Z, n, masks, inv_tau, block, grad_out, want_grad) -> dict:
+    """``SupConLoss1(exclude_other_pos=True)`` -- contrast_loss3.py:93-106.
+
+    E = exp(S - shift) (any common shift cancels), negsum_i = sum_{j in Q_i} E_ij,
+    r_i = q_i / (c_i + q_i) (:98), B_i = negsum_i / (r_i + 1e-4) (:100),
+    LLH_ij = (S_ij - shift) - log(E_ij + B_i) (:99-100, the +1e-16 dropped as in the default mode),
+    loss = -(1/N) sum_i (1/c_i) sum_{j in P_i} LLH_ij (:105-106).
+    dLoss/dS_ij = -(g/N) [ P_ij B_i / (c_i (E_ij + B_i)) - Q_ij E_ij v_i ],
+    v_i = (1/c_i) sum_{j in P_i} 1 / (E_ij + B_i) / (r_i + 1e-4).
+    """
+    N = 2 * n
+    shift = inv_tau
+    blocks = [(i0, min(i0 + block, N)) for i0 in range(0, N, block)]
+    c = np.empty(N)
+    q = np.empty(N)
+    negsum = np.empty(N)
+    for i0, i1 in blocks:
+        E = np.exp((Z[i0:i1] @ Z.T) * inv_tau - shift)
+        pos, valid = masks.rows(i0, i1)
+        neg = valid & ~pos
+        c[i0:i1] = pos.sum(axis=1)
+        q[i0:i1] = neg.sum(axis=1)
+        negsum[i0:i1] = np.where(neg, E, 0.0).sum(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rr = q / (c + q) + 1e-4
+        B = negsum / rr
+    wl = np.empty(N)
+    v = np.empty(N)
+    for i0, i1 in blocks:
+        S = (Z[i0:i1] @ Z.T) * inv_tau - shift
+        pos, _ = masks.rows(i0, i1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            den = np.exp(S) + B[i0:i1, None]
+            wl[i0:i1] = np.where(pos, S - np.log(den), 0.0).sum(axis=1)
+            v[i0:i1] = np.where(pos, 1.0 / den, 0.0).sum(axis=1) / (c[i0:i1] * rr[i0:i1])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        loss = -np.mean(wl / c)
+    out = dict(loss=float(loss), ratio=1.0, c=c, q=q, negsum=negsum, B=B, v=v, wl=wl, wp=c.copy(), scale=1.0)
+    if not want_grad:
+        return out
+    k = grad_out / N
+    dZ = np.empty_like(Z)
+    for i0, i1 in blocks:
+        E = np.exp((Z[i0:i1] @ Z.T) * inv_tau - shift)
+        pos, valid = masks.rows(i0, i1)
+        posT, validT = masks.cols_T(i0, i1)
+        neg, negT = valid & ~pos, validT & ~posT
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Bi, Bj = B[i0:i1, None], B[None, :]
+            dS_r = -k * (np.where(pos, Bi / (c[i0:i1, None] * (E + Bi)), 0.0) - np.where(neg, E * v[i0:i1, None], 0.0))
+            dS_c = -k * (np.where(posT, Bj / (c[None, :] * (E + Bj)), 0.0) - np.where(negT, E * v[None, :], 0.0))
         dZ[i0:i1] = ((dS_r + dS_c) @ Z) * inv_tau
     out["dz1"] = dZ[:n]
     out["dz2"] = dZ[n:]

@@ -58,6 +58,8 @@ def run_reference(ref, z1, z2, *, cls, target=None, mask=None, gamma=None, mode=
     b = z2.clone().requires_grad_(True)
     if cls == "SupConLoss1":
         crit = ref.SupConLoss1(temperature=temperature)
+    elif cls == "SupConLoss1Excl":
+        crit = ref.SupConLoss1(temperature=temperature, exclude_other_pos=True)
     else:
         crit = ref.SelfPacedSupConLoss(temperature=temperature, weight_update=mode, correct_grad=correct_grad)
         if gamma is not None:
@@ -163,5 +165,51 @@ def main():
     print("cfg2:", len(cases), "cases")
 
 
+def main_excl():
+    """SupConLoss1(exclude_other_pos=True) (:97-100) -> tests/golden/excl_cases.npz (kept apart from the files
+    above so that adding it does not rewrite them)."""
+    ref = load_reference()
+    wl = _load_workloads()
+    store, cases = {}, []
+
+    def add(name, z1, z2, **kw):
+        store[f"{name}/z1"], store[f"{name}/z2"] = z1.numpy().astype(np.float32), z2.numpy().astype(np.float32)
+        if kw.get("target") is not None:
+            store[f"{name}/labels"] = np.asarray(kw["target"])
+        if kw.get("mask") is not None:
+            store[f"{name}/tri_mask"] = kw["mask"].numpy()
+        store[f"{name}/temperature"] = np.float64(kw.get("temperature", 0.07))
+        res = run_reference(ref, z1, z2, cls="SupConLoss1Excl", **kw)
+        for k, v in res.items():
+            store[f"{name}/{k}"] = v
+        cases.append(name)
+
+    n, d = 64, 128
+    meta = wl.acdc_meta_labels(n)
+    z1, z2 = wl.make_views(meta["partition"], d, sigma=0.7, seed=0)
+    tri = torch.randint(0, 3, (n, n), generator=torch.Generator().manual_seed(7)).float()
+    tri.fill_diagonal_(1.0)
+    for key in ("partition", "patient", "cycle", "composite"):
+        add(f"n64_{key}", z1, z2, target=meta[key].tolist())
+    add("n64_simclr_none", z1, z2)
+    add("n64_trimask", z1, z2, mask=tri)
+    add("n64_partition_t0.2", z1, z2, target=meta["partition"].tolist(), temperature=0.2)
+    g = torch.Generator().manual_seed(3)
+    t1 = torch.nn.functional.normalize(torch.randn(5, 16, generator=g), dim=1)
+    t2 = torch.nn.functional.normalize(torch.randn(5, 16, generator=g), dim=1)
+    add("n5_ragged", t1, t2, target=[0, 1, 0, 2, 1])
+    n, d = 256, 256
+    meta = wl.acdc_meta_labels(n)
+    z1, z2 = wl.make_views(meta["patient"], d, sigma=0.7, seed=1)
+    add("n256_patient", z1, z2, target=meta["patient"].tolist())
+    store["cases"] = np.array(cases)
+    np.savez_compressed(OUT / "excl_cases.npz", **store)
+    print("excl:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "excl":
+        main_excl()
+    else:
+        main()
+        main_excl()

@@ -15,7 +15,7 @@ _PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get("SPCL_B200_LIB", _PKG_DIR / "libspcl_b200.so"))   # override: kernel A/B builds
 BUILD_SCRIPT = _PKG_DIR / "csrc" / "build.sh"
 
-MODE_NONE, MODE_HARD, MODE_SOFT = 0, 1, 2
+MODE_NONE, MODE_HARD, MODE_SOFT, MODE_EXCL = 0, 1, 2, 3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 TILE = 128
 MAX_D = 256

@@ -8,6 +8,9 @@
 //   forward : one CTA owns 64 anchor rows and sweeps all columns twice
 //             sweep 1: rowsum_i = sum_{j in M_i} exp(S_ij - 1/tau), c_i            (:180-182)
 //             sweep 2: sum_j P W LLH, sum_j P W with W from the final logD_i       (:184-197, :207-214)
+//             SPCL_MODE_EXCL (SupConLoss1 exclude_other_pos, :97-100): sweep 1 sums the NEGATIVES only and
+//             counts them, B_i = negsum_i / (q_i / (c_i + q_i) + 1e-4); sweep 2 sums, over the positives,
+//             S_ij - 1/tau - log(E_ij + B_i) and 1 / (E_ij + B_i)
 //   backward: one CTA owns 64 anchor rows; per column tile it forms
 //             T_ij = M_ij E_ij u_i - P_ij W_ij / c_i  +  (same with i <-> j)
 //             in shared memory and accumulates dZ_I += T_IJ Z_J in registers.
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row
 
   float rowsum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, spx[4] = {0.f, 0.f, 0.f, 0.f};
   float acc[4][4];
+  const bool excl = p.mode == SPCL_MODE_EXCL;   // spx counts the negatives in this mode
 
   // ---- sweep 1: denominators and positive counts ----
   for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
@@ -124,6 +128,14 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row
         bool pos, valid;
         pair_flags(p, gi[a], gj, li[a], lj, pos, valid);
         const float s = acc[a][b] * p.inv_tau;
+        if (excl) {
+          if (valid && !pos) {
+            rowsum[a] += expf(s - shift);
+            spx[a] += 1.f;
+          }
+          if (pos) cnt[a] += 1.f;
+          continue;
+        }
         if (valid) rowsum[a] += expf(s - shift);
         if (pos) {
           cnt[a] += 1.f;
@@ -141,6 +153,15 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row
     logD[a] = shift + logf(rowsum[a]);
     wl[a] = spx[a] - cnt[a] * logD[a];   // mode NONE: sum_j P (S - logD)
     wp[a] = cnt[a];
+  }
+  // EXCL: rr_i = neg_ratio_i + 1e-4 (:98, :100) and B_i (kept in logD[])
+  float rr[4] = {1.f, 1.f, 1.f, 1.f};
+  if (excl) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      rr[a] = spx[a] / (cnt[a] + spx[a]) + 1e-4f;
+      logD[a] = rowsum[a] / rr[a];
+    }
   }
 
   // ---- sweep 2: self-paced weighted sums (needs the final logD) ----
@@ -160,6 +181,13 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row
           bool pos, valid;
           pair_flags(p, gi[a], gj, li[a], lj, pos, valid);
           if (!pos) continue;
+          if (excl) {
+            const float sh = acc[a][b] * p.inv_tau - shift;
+            const float den = expf(sh) + logD[a];
+            wl[a] += sh - logf(den);
+            wp[a] += 1.f / den;
+            continue;
+          }
           const float llh = acc[a][b] * p.inv_tau - logD[a];
           const float w = sp_weight(-llh, p.gamma, p.inv_gamma, p.mode);
           wl[a] = fmaf(w, llh, wl[a]);
@@ -182,8 +210,10 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args p, float* __restrict__ row
       float l = 0.f, w = 0.f, c = 0.f;
       if (gi[a] < p.row_end) {
         const float invc = 1.f / cnt[a];          // c == 0 -> inf -> NaN loss, like the reference's 0/0
-        const float A = wp[a] * invc;
-        const float u = A * expf(shift - logD[a]);
+        // EXCL: plane 0 = B_i, plane 2 = 1, plane 3 = v_i = (1/c_i) sum_P 1 / (E + B_i) / rr_i
+        const float A = excl ? 1.f : wp[a] * invc;
+        const float u = excl ? wp[a] * invc / rr[a] : A * expf(shift - logD[a]);
+        if (excl) wp[a] = cnt[a];
         row_stats[gi[a]] = logD[a];
         row_stats[sld + gi[a]] = invc;
         row_stats[2 * sld + gi[a]] = A;
@@ -256,6 +286,15 @@ __global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float* __restrict
           else { pos_ji = pos_ij; val_ji = val_ij; }
           const float s = acc[a][b] * p.inv_tau;
           const float e = expf(s - shift);
+          if (p.mode == SPCL_MODE_EXCL) {
+            // T = Q E (v_i + v_j) - P (B_i / (c_i (E + B_i)) + B_j / (c_j (E + B_j)))
+            if (val_ij && !pos_ij) t = fmaf(e, si[a].w, t);
+            if (val_ji && !pos_ji) t = fmaf(e, sj.w, t);
+            if (pos_ij) t -= si[a].y * si[a].x / (e + si[a].x);
+            if (pos_ji) t -= sj.y * sj.x / (e + sj.x);
+            ts[ty * 4 + a][cj] = t;
+            continue;
+          }
           if (val_ij) t = fmaf(e, si[a].w, t);
           if (val_ji) t = fmaf(e, sj.w, t);
           if (pos_ij) t -= sp_weight(si[a].x - s, p.gamma, p.inv_gamma, p.mode) * si[a].y;
@@ -315,8 +354,8 @@ static int check_common(const float* z, int64_t n_total, int32_t d, int64_t ldz,
   if ((labels == nullptr) == (tri == nullptr)) return SPCL_ERR_INVALID_ARG;
   if (tri != nullptr && n_half * 2 != n_total) return SPCL_ERR_INVALID_ARG;
   if (row_begin < 0 || row_end > n_total || row_begin >= row_end) return SPCL_ERR_INVALID_ARG;
-  if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_SOFT) return SPCL_ERR_INVALID_ARG;
-  if (mode != SPCL_MODE_NONE && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
+  if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_EXCL) return SPCL_ERR_INVALID_ARG;
+  if ((mode == SPCL_MODE_HARD || mode == SPCL_MODE_SOFT) && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
   return SPCL_OK;
 }
 

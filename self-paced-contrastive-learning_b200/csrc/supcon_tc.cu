@@ -1435,6 +1435,7 @@ static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad,
   if (row_begin < 0 || row_end > n_total || row_begin >= row_end) return SPCL_ERR_INVALID_ARG;
   if (row_begin % TILE != 0) return SPCL_ERR_UNSUPPORTED;
   if (n_pad > (1LL << 31) - 2 * TILE) return SPCL_ERR_UNSUPPORTED;
+  if (mode == SPCL_MODE_EXCL) return SPCL_ERR_UNSUPPORTED;   // exclude_other_pos runs on the fp32 path only
   if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_SOFT) return SPCL_ERR_INVALID_ARG;
   // exp(S - 1/tau) must stay a normal fp32 for S >= -1/tau
   if (inv_tau > 40.f) return SPCL_ERR_UNSUPPORTED;   // also keeps the exponent splice of ex2_poly2 in range

@@ -42,7 +42,12 @@ def is_normalized(feature: Tensor, dim: int = 1) -> bool:
     return bool(torch.allclose(norms, torch.ones_like(norms)))
 
 
-def _pick_tc(precision: str, N: int, has_tri: bool) -> bool:
+def _pick_tc(precision: str, N: int, has_tri: bool, mode: int = nat.MODE_NONE) -> bool:
+    if mode == nat.MODE_EXCL:
+        # exclude_other_pos (:97-100) has a per-pair denominator; it is carried by the fp32 kernels only
+        if precision == "bf16":
+            raise nat.SpclError("exclude_other_pos=True runs on the fp32 path only (precision='fp32' or 'auto')")
+        return False
     if precision == "bf16":
         return True
     if precision == "fp32":
@@ -94,7 +99,7 @@ class _Diagnostics:
             z = torch.cat([self.z1, self.z2]).float()
             llh = (z @ z.t()) / self.t - self.row_stats[0, :N, None]
             l = -llh
-            if self.mode == nat.MODE_NONE:
+            if self.mode in (nat.MODE_NONE, nat.MODE_EXCL):
                 w = torch.ones_like(l)
             elif self.mode == nat.MODE_HARD:
                 w = (l <= self.gamma).float()
@@ -124,7 +129,7 @@ def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Op
         labels = ops.label_codes(target, n, dev)
     else:                                     # :140-143  SimCLR
         labels = torch.arange(n, dtype=torch.int32, device=dev)
-    use_tc = _pick_tc(precision, 2 * n, tri is not None)
+    use_tc = _pick_tc(precision, 2 * n, tri is not None, int(mode))
     scalars, row_stats, _, _, _ = ops.supcon_fwd(z1, z2, labels, tri, float(temperature), float(gamma), int(mode),
                                                  bool(correct_grad), use_tc)
     return scalars[0], scalars, dict(labels=labels, tri=tri, row_stats=row_stats, use_tc=use_tc)
@@ -179,14 +184,11 @@ class SupConLoss1(_FusedSupConBase):
 
     def __init__(self, temperature=0.07, exclude_other_pos=False, **kwargs):
         super().__init__()
-        if exclude_other_pos:
-            # :97-100; default off and never enabled by any caller (infonce.py:93) -- SURVEY.md section 8 row f3
-            raise NotImplementedError("exclude_other_pos=True is not implemented in the fused kernels yet")
         self._init_common(temperature, kwargs)
-        self._exclude_pos = False
+        self._exclude_pos = bool(exclude_other_pos)      # :97-100 (fp32 kernels, any N)
 
     def _gamma_mode_cg(self):
-        return 1e6, nat.MODE_NONE, False
+        return 1e6, (nat.MODE_EXCL if self._exclude_pos else nat.MODE_NONE), False
 
 
 class SelfPacedSupConLoss(_FusedSupConBase):

@@ -75,3 +75,13 @@ def parse_cfg1_case(name, g):
             if key in parts:
                 kw["target"] = g["labels_" + key].tolist()
     return kw
+
+
+def excl_case_inputs(g, name):
+    """inputs of one ``excl_cases.npz`` case (SupConLoss1(exclude_other_pos=True), oracle/make_golden.py)."""
+    kw = dict(temperature=float(g[f"{name}/temperature"]), target=None, mask=None)
+    if f"{name}/tri_mask" in g:
+        kw["mask"] = g[f"{name}/tri_mask"]
+    elif f"{name}/labels" in g:
+        kw["target"] = g[f"{name}/labels"].tolist()
+    return g[f"{name}/z1"], g[f"{name}/z2"], kw

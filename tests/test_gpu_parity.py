@@ -9,7 +9,7 @@ from spcl_b200 import _native as nat
 from spcl_b200.workloads import acdc_meta_labels, make_views, make_workload
 from oracle.closed_form import supcon_closed_form
 from oracle.dense_port import dense_supcon
-from conftest import Golden, parse_cfg1_case
+from conftest import Golden, excl_case_inputs, parse_cfg1_case
 from torch_ref import supcon_ref64
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 CFG1 = Golden("cfg1_n64_d128.npz")
 TINY = Golden("tiny_n5_d16.npz")
 CFG2 = Golden("cfg2_n256_d256.npz")
+EXCL = Golden("excl_cases.npz")
 MODE = {"none": nat.MODE_NONE, "hard": nat.MODE_HARD, "soft": nat.MODE_SOFT}
 
 # ---- stated tolerances -------------------------------------------------------------------------
@@ -33,8 +34,9 @@ def _run(z1, z2, *, cls="SP", target=None, mask=None, gamma=1e6, mode="hard", co
          temperature=0.07, precision="fp32", validate=True):
     a = torch.as_tensor(z1).cuda().requires_grad_(True)
     b = torch.as_tensor(z2).cuda().requires_grad_(True)
-    if cls == "SupConLoss1":
-        crit = spcl_b200.SupConLoss1(temperature=temperature, precision=precision, validate=validate)
+    if cls in ("SupConLoss1", "SupConLoss1Excl"):
+        crit = spcl_b200.SupConLoss1(temperature=temperature, exclude_other_pos=cls == "SupConLoss1Excl",
+                                     precision=precision, validate=validate)
     else:
         crit = spcl_b200.SelfPacedSupConLoss(temperature=temperature, weight_update=mode, correct_grad=correct_grad,
                                              precision=precision, validate=validate)
@@ -46,7 +48,7 @@ def _run(z1, z2, *, cls="SP", target=None, mask=None, gamma=1e6, mode="hard", co
         kw["target"] = torch.as_tensor(target).cuda() if isinstance(target, np.ndarray) else target
     loss = crit(a, b, **kw)
     loss.backward()
-    ratio = crit.downgrade_ratio if cls != "SupConLoss1" else float("nan")
+    ratio = crit.downgrade_ratio if cls == "SP" else float("nan")
     return dict(loss=loss.item(), ratio=ratio, dz1=a.grad.cpu().numpy(), dz2=b.grad.cpu().numpy(), crit=crit)
 
 
@@ -63,6 +65,30 @@ def _grad_metrics(res, ref):
 # ------------------------------------------------------------------------------------------------
 # fp32 path vs the reference's own outputs
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", EXCL.cases)
+def test_exclude_other_pos_matches_reference(name):
+    """SupConLoss1(exclude_other_pos=True), contrast_loss3.py:97-100, against the reference's own outputs."""
+    z1, z2, kw = excl_case_inputs(EXCL, name)
+    res = _run(z1, z2, cls="SupConLoss1Excl", precision="auto", **kw)
+    ref = EXCL.case(name)
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL), (res["loss"], ref["loss"])
+    rel, _ = _grad_metrics(res, ref)
+    assert rel <= FP32_GRAD_REL, rel
+
+
+def test_exclude_other_pos_large_n_uses_fp32_kernels():
+    """N = 2048 >= the auto threshold still runs (fp32 kernels) and matches the fp64 oracle; bf16 is refused."""
+    labels = acdc_meta_labels(1024)["patient"]
+    z1, z2 = make_views(labels, 64, sigma=0.7, seed=4)
+    res = _run(z1, z2, cls="SupConLoss1Excl", target=labels.tolist(), precision="auto")
+    ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), mode="excl")
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL)
+    rel, _ = _grad_metrics(res, ref)
+    assert rel <= FP32_GRAD_REL, rel
+    with pytest.raises(nat.SpclError):
+        _run(z1, z2, cls="SupConLoss1Excl", target=labels.tolist(), precision="bf16")
+
+
 @pytest.mark.parametrize("name", CFG1.cases)
 def test_fp32_path_matches_reference_cfg1(name):
     kw = parse_cfg1_case(name, CFG1)

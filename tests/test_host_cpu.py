@@ -101,8 +101,11 @@ def test_module_surface_matches_reference():
     assert repr(sp) == "SelfPacedSupConLoss with T: 0.1, method: soft gamma: 3.0"
     s1 = spcl_b200.SupConLoss1()
     assert s1._t == 0.07
-    with pytest.raises(NotImplementedError):
-        spcl_b200.SupConLoss1(exclude_other_pos=True)
+    sx = spcl_b200.SupConLoss1(exclude_other_pos=True)          # :35, :97-100
+    assert sx._exclude_pos is True and sx._gamma_mode_cg()[1] == spcl_b200._native.MODE_EXCL
+    with pytest.raises(spcl_b200._native.SpclError):            # exclude_other_pos is an fp32-path mode
+        spcl_b200.losses._pick_tc("bf16", 4096, False, spcl_b200._native.MODE_EXCL)
+    assert spcl_b200.losses._pick_tc("auto", 1 << 15, False, spcl_b200._native.MODE_EXCL) is False
     with pytest.raises(AttributeError):
         _ = sp.downgrade_ratio                       # only after a forward call
 

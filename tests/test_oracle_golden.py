@@ -9,11 +9,12 @@ import torch
 
 from oracle.closed_form import codes_from_target, supcon_closed_form
 from oracle.dense_port import dense_supcon
-from conftest import Golden, parse_cfg1_case
+from conftest import Golden, excl_case_inputs, parse_cfg1_case
 
 CFG1 = Golden("cfg1_n64_d128.npz")
 TINY = Golden("tiny_n5_d16.npz")
 CFG2 = Golden("cfg2_n256_d256.npz")
+EXCL = Golden("excl_cases.npz")
 
 # fp64 closed form vs the fp32 reference: the reference's own rounding is the floor.
 LOSS_RTOL = 2e-5
@@ -73,6 +74,27 @@ def test_closed_form_cfg2(name):
     res = supcon_closed_form(CFG2[f"{name}/z1"], CFG2[f"{name}/z2"], target=CFG2[f"{name}/labels"].tolist(),
                              gamma=float(CFG2[f"{name}/gamma"]), mode="soft", block=128)
     _check(res, CFG2.case(name))
+
+
+@pytest.mark.parametrize("name", EXCL.cases)
+def test_closed_form_exclude_other_pos(name):
+    z1, z2, kw = excl_case_inputs(EXCL, name)
+    res = supcon_closed_form(z1, z2, mode="excl", **kw)
+    _check(res, EXCL.case(name))
+
+
+@pytest.mark.parametrize("name", EXCL.cases)
+def test_dense_port_exclude_other_pos(name):
+    z1, z2, kw = excl_case_inputs(EXCL, name)
+    a = torch.from_numpy(z1).requires_grad_(True)
+    b = torch.from_numpy(z2).requires_grad_(True)
+    if kw["mask"] is not None:
+        kw["mask"] = torch.from_numpy(kw["mask"])
+    out = dense_supcon(a, b, mode="excl", **kw)
+    out.loss.backward()
+    res = dict(loss=out.loss.item(), ratio=float("nan"), dz1=a.grad.numpy(), dz2=b.grad.numpy())
+    ref = dict(EXCL.case(name), ratio=np.float64("nan"))
+    _check(res, ref, loss_rtol=1e-6, grad_rel=1e-5)
 
 
 def test_identities():
