@@ -354,3 +354,45 @@ def test_l2norm_zero_row_uses_eps_like_torch():
     x = torch.zeros(4, 16).cuda(); x[1] = 1.0
     y = spcl_b200.normalize(x)
     assert torch.equal(y[0], torch.zeros(16).cuda()) and torch.allclose(y, F.normalize(x))
+
+
+# ------------------------------------------------------------------------------------------------
+# host-buffer front end (bench.py's e2e leg)
+# ------------------------------------------------------------------------------------------------
+def test_hostfeed_matches_direct_calls():
+    """Staged (copy-stream) batches give the same losses / gradients as plain .cuda() calls, in order."""
+    n, d, steps = 640, 128, 5
+    labels = acdc_meta_labels(n)["patient"].to(torch.int32)
+    batches = [make_views(labels, d, sigma=0.7, seed=s) for s in range(steps)]
+    crit = spcl_b200.SelfPacedSupConLoss(weight_update="soft", precision="bf16", check_nan=False, validate=False)
+    crit.set_gamma(6.0)
+    want, want_g = [], []
+    for z1, z2 in batches:
+        a = z1.cuda().requires_grad_(True)
+        b = z2.cuda().requires_grad_(True)
+        loss = crit(a, b, target=labels.cuda())
+        loss.backward()
+        want.append(loss.item())
+        want_g.append(a.grad.clone())
+    feed = spcl_b200.HostFeed(n, d, "cuda", depth=2)
+    pinned = [(z1.pin_memory(), z2.pin_memory()) for z1, z2 in batches]
+    lab_h = labels.pin_memory()
+    got_g = []
+    feed.push(*pinned[0], lab_h)
+    for k in range(steps):
+        if k + 1 < steps:
+            feed.push(*pinned[k + 1], lab_h)
+        a, b, lab, slot = feed.pop()
+        loss = crit(a, b, target=lab)
+        loss.backward()
+        got_g.append(a.grad)
+        feed.release(slot, loss)
+    got = feed.losses()
+    assert feed.h2d_bytes == steps * (2 * n * d * 4 + n * 4)
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    for g, w in zip(got_g, want_g):
+        # dZ is accumulated with atomics: same terms, different order
+        assert (g - w).abs().max().item() <= 1e-5 * w.abs().max().item()
+    with pytest.raises(RuntimeError):
+        for _ in range(3):
+            feed.push(*pinned[0], lab_h)
