@@ -292,6 +292,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers, 16 lanes x 32 columns in the "matrix fragment" layout: thread t receives
+//   v[4 r + 2 k + c] = (lane base + t / 4 + 8 k, column base + 8 r + 2 (t % 4) + c),  r < 4, k < 2, c < 2,
+// so a column is spread over only 8 threads (x 2 lanes each) and a lane over 4 threads: column sums need a 3-step
+// butterfly instead of the 5-step one of the 32x32b shape.  The address's lane field selects which 16 lanes
+// (warp quadrant base or base + 16).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 // TMEM -> registers: this thread's lane, 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

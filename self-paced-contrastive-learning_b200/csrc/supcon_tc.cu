@@ -86,6 +86,7 @@ struct Params {
   int64_t lddz;
   unsigned long long* trace;   // debug timeline (CTA 0), normally nullptr
   int dbg;                     // debug experiment switches (tools/gpu_exp.py), normally 0
+  int sym;                     // stats pass visits only tiles on / right of the diagonal block (square launches)
 };
 
 // debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
@@ -162,20 +163,66 @@ __device__ __forceinline__ void cta_range(const Params& p, int64_t& f0, int64_t&
   f1 = total * (blockIdx.x + 1) / gridDim.x;
 }
 
+// Symmetric stats pass: S, the exponentials and the label masks are symmetric, so row block I only visits the
+// column tiles that reach its diagonal block or lie right of it (first tile = I * TILE / bn) and every block
+// right of the diagonal also yields the COLUMN sums, which are the row statistics of the mirrored block.
+// sym_prefix = number of tiles of row blocks [0, I).
+__host__ __device__ inline int64_t sym_first_tile(int64_t I, int bn) { return bn == 2 * TILE ? (I >> 1) : I; }
+__host__ __device__ inline int64_t sym_prefix(int64_t I, int64_t CT, int bn) {
+  return bn == 2 * TILE ? I * CT - ((I - 1) * (I - 1)) / 4 : I * CT - (I * (I - 1)) / 2;
+}
+
+struct CtaRange {
+  int64_t I0;        // first row block (relative to row_begin)
+  uint32_t t0, n;    // first column tile inside it, number of tiles
+};
+
+__device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
+  CtaRange r;
+  if (!p.sym) {
+    int64_t f0, f1;
+    cta_range(p, f0, f1);
+    r.I0 = f0 / p.CT;
+    r.t0 = static_cast<uint32_t>(f0 % p.CT);
+    r.n = static_cast<uint32_t>(f1 - f0);
+    return r;
+  }
+  const int64_t total = sym_prefix(p.RB, p.CT, bn);
+  const int64_t f0 = total * blockIdx.x / gridDim.x, f1 = total * (blockIdx.x + 1) / gridDim.x;
+  int64_t lo = 0, hi = p.RB - 1;                 // largest I with sym_prefix(I) <= f0
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (sym_prefix(mid, p.CT, bn) <= f0) lo = mid; else hi = mid - 1;
+  }
+  r.I0 = lo;
+  r.t0 = static_cast<uint32_t>(sym_first_tile(lo, bn) + (f0 - sym_prefix(lo, p.CT, bn)));
+  r.n = static_cast<uint32_t>(f1 - f0);
+  return r;
+}
+
 // Walks the CTA's flattened tile range one tile at a time; a "segment" is the part of one row block.
 // 32-bit state: the per-tile bookkeeping of the single-thread roles sits on the critical path.
 struct TileCursor {
-  uint32_t t, CT, it, n, seg;
+  uint32_t t, CT, it, n, seg, tfirst, I;
+  int symshift;      // < 0: every row block starts at tile 0; else row block I starts at tile I >> symshift
   __device__ __forceinline__ TileCursor(int64_t f0, int64_t f1, int64_t ct)
       : t(static_cast<uint32_t>(f0 % ct)), CT(static_cast<uint32_t>(ct)), it(0), n(static_cast<uint32_t>(f1 - f0)),
-        seg(0) {}
+        seg(0), tfirst(0), I(0), symshift(-1) {}
+  __device__ __forceinline__ TileCursor(const CtaRange& r, int64_t ct, int symshift_)
+      : t(r.t0), CT(static_cast<uint32_t>(ct)), it(0), n(r.n), seg(0),
+        tfirst(symshift_ >= 0 ? static_cast<uint32_t>(r.I0) >> symshift_ : 0u), I(static_cast<uint32_t>(r.I0)),
+        symshift(symshift_) {}
   __device__ __forceinline__ bool valid() const { return it < n; }
-  __device__ __forceinline__ bool first() const { return it == 0 || t == 0; }
+  __device__ __forceinline__ bool first() const { return it == 0 || t == tfirst; }
   __device__ __forceinline__ bool last() const { return it + 1 == n || t + 1 == CT; }
   __device__ __forceinline__ void next() {
     if (last()) ++seg;
     ++it;
-    if (++t == CT) t = 0;
+    if (++t == CT) {
+      ++I;
+      tfirst = symshift >= 0 ? I >> symshift : 0u;
+      t = tfirst;
+    }
   }
 };
 
@@ -331,6 +378,99 @@ __device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch
   }
 }
 
+// ---- symmetric stats pass: the same tile also yields the sums over its ROWS for every column ----
+// Transposing butterfly: v[c] = this lane's value for column c; returns the sum over the 32 lanes for column
+// `lane` (31 shuffles).  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(kFullMask, send, s);
+    }
+  }
+  return v[0];
+}
+
+// fast: every element is a valid negative.  lo / hi are the 16x256b fragments (ptx::tmem_ld_16x256b_x4) of lanes
+// [0, 16) / [16, 32) of the warp's TMEM quadrant for 32 columns: this thread holds rows 16 h + 8 k + lane / 4 and
+// columns 8 r + 2 (lane % 4) + {0, 1}.  racc[2 h + k] += E (row partials, two columns per instruction); returns
+// the sum over the warp's 32 rows for column  16 b4 + 8 b3 + 2 (lane % 4) + b2  (b_i = bit i of lane): four adds
+// per column in the thread, then a 3-step butterfly over the 8 threads that share the column (7 shuffles).
+__device__ __forceinline__ float stats_chunk_sym(const uint32_t (&lo)[16], const uint32_t (&hi)[16], const ExpK& k,
+                                                 uint64_t (&racc)[4], int lane) {
+  uint64_t col[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    uint64_t e[4];
+#pragma unroll
+    for (int hk = 0; hk < 4; ++hk) {
+      const int i = 4 * r + 2 * (hk & 1);
+      const uint64_t d2 = (hk & 2) ? pack_u32x2(hi[i], hi[i + 1]) : pack_u32x2(lo[i], lo[i + 1]);
+      e[hk] = use_poly(4 * r + hk, SPCL_FWD_POLY_PAIRS) ? ex2_poly2<4>(d2, k) : ex2_mufu2(d2, k);
+      racc[hk] = add_f32x2(racc[hk], e[hk]);
+    }
+    col[r] = add_f32x2(add_f32x2(e[0], e[1]), add_f32x2(e[2], e[3]));
+  }
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  // xor 16: keep column groups r = 2 b4 + {0, 1}
+  uint64_t k0 = b4 ? col[2] : col[0], k1 = b4 ? col[3] : col[1];
+  const uint64_t s0 = b4 ? col[0] : col[2], s1 = b4 ? col[1] : col[3];
+  k0 = add_f32x2(k0, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(s0), 16));
+  k1 = add_f32x2(k1, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(s1), 16));
+  // xor 8: keep r = 2 b4 + b3
+  uint64_t kk = b3 ? k1 : k0;
+  const uint64_t ss = b3 ? k0 : k1;
+  kk = add_f32x2(kk, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(ss), 8));
+  // xor 4: keep c = b2
+  float c0, c1;
+  unpack_f32x2(kk, c0, c1);
+  const float kf = b2 ? c1 : c0, sf = b2 ? c0 : c1;
+  return kf + __shfl_xor_sync(kFullMask, sf, 4);
+}
+
+// slow + column sums (tiles right of the diagonal that may hold positives, tail block): 32x32b layout, this
+// thread = one row.  Column `lane` of the chunk gets its three sums over the warp's rows, accumulated into the
+// mirrored rows' acc entries.
+__device__ __forceinline__ void stats_chunk_slow_sym(const uint32_t (&v)[32], int ch, int jmax, int li, bool row_ok,
+                                                     const int32_t* __restrict__ lab, float c2, bool want_spx,
+                                                     float4* __restrict__ acc_cols, int lane, float& rowsum,
+                                                     float& cnt, float& spx) {
+  float ev[32], pv[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int cidx = ch * 32 + e;
+    const float dot = __uint_as_float(v[e]);
+    const bool valid = cidx < jmax;                 // no diagonal right of the diagonal block
+    const bool pos = valid && (__ldg(lab + cidx) == li);
+    const float ex = ex2_approx(fmaf(dot, c2, -c2));
+    rowsum += valid ? ex : 0.f;
+    cnt += pos ? 1.f : 0.f;
+    spx += pos ? dot : 0.f;
+    ev[e] = (valid && row_ok) ? ex : 0.f;
+    pv[e] = (pos && row_ok) ? 1.f : 0.f;
+  }
+  const float ce = warp_colsum32(ev, lane);
+  const float cp = warp_colsum32(pv, lane);
+  float* a = reinterpret_cast<float*>(acc_cols + ch * 32 + lane);
+  if (ce != 0.f) atomicAdd(a + 0, ce);
+  if (cp != 0.f) atomicAdd(a + 1, cp);
+  if (want_spx && __any_sync(kFullMask, cp != 0.f)) {      // warp-uniform: the butterfly needs every lane
+    float dv[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int cidx = ch * 32 + e;
+      const bool pos = row_ok && (cidx < jmax) && (__ldg(lab + cidx) == li);
+      dv[e] = pos ? __uint_as_float(v[e]) : 0.f;
+    }
+    const float cd = warp_colsum32(dv, lane);
+    if (cd != 0.f) atomicAdd(a + 2, cd);
+  }
+}
+
 __device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
                                          const int32_t* lab_s, const Params& p, float logD, float& wl, float& wp) {
 #pragma unroll
@@ -401,7 +541,7 @@ __device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, 
 // =================================================================================================
 // forward, pass A: row statistics over all column tiles
 // =================================================================================================
-template <int BN>
+template <int BN, bool SYM>
 __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                             const __grid_constant__ CUtensorMap tmap_b, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -425,9 +565,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
   const uint32_t tmem_base = bar->tmem_base;
   const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
 
-  int64_t f0, f1;
-  cta_range(p, f0, f1);
-  const int64_t rb0 = p.row_begin / TILE, I0 = f0 / p.CT;
+  const CtaRange range = cta_range_of(p, BN);
+  constexpr int kSymShift = SYM ? (kSub == 2 ? 1 : 0) : -1;
+  const int64_t rb0 = p.row_begin / TILE, I0 = range.I0;
   const uint32_t a_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
   const uint32_t slot_tx = static_cast<uint32_t>(p.dc) * BN * 128;
 
@@ -435,7 +575,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       Ring rs(p.nslot);
-      for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next()) {
+      for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rs.next()) {
         if (c.first()) {
           const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
           mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
@@ -470,7 +610,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     const uint32_t a_base = smem_u32(sm.a_tile);
     const int nk = p.dc * 4;
     Ring rs(p.nslot), rb(kBufs);
-    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rs.next(), rb.next()) {
+    for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rs.next(), rb.next()) {
       if ((c.it & 1) != mw) continue;
       if (lane == 0) {
         if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
@@ -494,6 +634,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
   } else if (warp < kEpilogueWarps) {
     // ------------------------------- epilogue -----------------------------------
     // BN = 256: both warpgroups work on every tile, one 128-column block each.  BN = 128: they alternate tiles.
+    // SYM: blocks left of the diagonal block are skipped (their row block produced these sums as column sums),
+    // the diagonal block gives row sums only, blocks right of it give row AND column sums.
     const int wg = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -502,8 +644,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     bool row_ok = false;
     int li = 0;
     int4 rsig = make_int4(0, 0, 0, 0);
-    uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};       // fast path: packed partial row sums
+    uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};       // fast path: packed partial row sums (SYM: one per held row)
     float s0 = 0.f, cnt = 0.f, spx = 0.f;              // slow path: rowsum, positives, sum P dot
+    // SYM fast path: column this lane ends up with after the butterfly, row it flushes at the end of a segment
+    const int sym_col = (lane & 16) + (lane & 8) + 2 * (lane & 3) + ((lane >> 2) & 1);
+    const int sym_row = q * 32 + 16 * ((lane >> 1) & 1) + 8 * (lane & 1) + (lane >> 2);
 
     // Which tiles need the generic path (diagonal, tail, possible positives) is decided for 32 column tiles at a
     // time, one tile per lane, and kept as a warp-uniform bit mask: with two warps per scheduler every
@@ -521,7 +666,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     };
     uint32_t mask = 0, mask_grp = 0xffffffffu;
     Ring rb(kBufs);
-    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), rb.next()) {
+    for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rb.next()) {
       if (c.first()) {
         gi0 = p.row_begin + (I0 + c.seg) * TILE;
         gi = gi0 + r;
@@ -542,28 +687,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
         const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
         const uint32_t jb = block_of(c.t);
         const int64_t j0 = static_cast<int64_t>(jb) * TILE;
-        const bool inside = jb < ct128;
+        const bool inside = jb < ct128 && !(SYM && jb < row_jb);
+        const bool cols = SYM && jb > row_jb;
         mbar_wait_warp(&bar->s_full[buf], bph, lane);
         TRACE(2 + warp, c.it, 0);
         tc_fence_after();
         if (inside && !(p.dbg & 2)) {
-          const int64_t dj = gi - j0;
-          const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
-          const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
-          const int32_t* lab = p.labels + j0;
           const uint32_t taddr = lane_base + buf * BN + (kSub == 2 ? wg * TILE : 0);
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32b_x32(taddr, va);
-          tmem_wait_ld();
+          if (SYM && cols && !slow) {
+            // fragment loads of the two 16-lane halves, double buffered like the row layout below
+            uint32_t la[16], ha[16], lb[16], hb[16];
+            float* colacc = reinterpret_cast<float*>(p.acc + j0 + sym_col);
+            tmem_ld_16x256b_x4(taddr, la);
+            tmem_ld_16x256b_x4(taddr + (16u << 16), ha);
+            tmem_wait_ld();
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-            uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
-            if (p.dbg & 1) acc2[ch] ^= cur[ch];
-            else if (!slow) stats_chunk_fast(cur, ek, acc2);
-            else stats_chunk_slow(cur, ch, jdiag, jmax, li, lab, p.c2, s0, cnt, spx);
-            if (ch < 3) tmem_wait_ld();
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t(&cl)[16] = (ch & 1) ? lb : la;
+              uint32_t(&chh)[16] = (ch & 1) ? hb : ha;
+              uint32_t(&nl)[16] = (ch & 1) ? la : lb;
+              uint32_t(&nh)[16] = (ch & 1) ? ha : hb;
+              if (ch < 3) {
+                tmem_ld_16x256b_x4(taddr + (ch + 1) * 32, nl);
+                tmem_ld_16x256b_x4(taddr + (16u << 16) + (ch + 1) * 32, nh);
+              }
+              const float cs = stats_chunk_sym(cl, chh, ek, acc2, lane);
+              atomicAdd(colacc + ch * 32 * 4, cs);               // acc is float4 per anchor: .x = rowsum
+              if (ch < 3) tmem_wait_ld();
+            }
+          } else {
+            const int64_t dj = gi - j0;
+            const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+            const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
+            const int32_t* lab = p.labels + j0;
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr, va);
+            tmem_wait_ld();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+              uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+              if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
+              if (p.dbg & 1) acc2[ch] ^= cur[ch];
+              else if (SYM && cols)
+                stats_chunk_slow_sym(cur, ch, jmax, li, row_ok, lab, p.c2, p.mode == SPCL_MODE_NONE, p.acc + j0, lane,
+                                     s0, cnt, spx);
+              else if (!SYM && !slow) stats_chunk_fast(cur, ek, acc2);
+              else stats_chunk_slow(cur, ch, jdiag, jmax, li, lab, p.c2, s0, cnt, spx);
+              if (ch < 3) tmem_wait_ld();
+            }
           }
         }
         tc_fence_before();
@@ -572,13 +744,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
         TRACE(2 + warp, c.it, 1);
       }
       if (c.last()) {
+        if (SYM) {
+          // fast-path row partials: row 16 h + 8 k + lane / 4 is spread over the 4 threads of a quad
+          float mine_sum = 0.f;
+#pragma unroll
+          for (int hk = 0; hk < 4; ++hk) {
+            float lo, hi;
+            unpack_f32x2(acc2[hk], lo, hi);
+            float t = lo + hi;
+            t += __shfl_xor_sync(kFullMask, t, 1);
+            t += __shfl_xor_sync(kFullMask, t, 2);
+            if ((lane & 3) == hk) mine_sum = t;
+          }
+          const int64_t grow = gi0 + sym_row;
+          if (grow < p.row_end && mine_sum != 0.f) atomicAdd(reinterpret_cast<float*>(p.acc + grow), mine_sum);
+        }
         if (row_ok) {
           float* a = reinterpret_cast<float*>(p.acc + gi);
-          float lo, hi, rowsum = s0;
+          float rowsum = s0;
+          if (!SYM) {
+            float lo, hi;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            unpack_f32x2(acc2[k], lo, hi);
-            rowsum += lo + hi;
+            for (int k = 0; k < 4; ++k) {
+              unpack_f32x2(acc2[k], lo, hi);
+              rowsum += lo + hi;
+            }
           }
           if (rowsum != 0.f) atomicAdd(a + 0, rowsum);
           if (cnt != 0.f) atomicAdd(a + 1, cnt);
@@ -1421,6 +1611,16 @@ static bool pair_enabled() {
   return env != 0 && !(g_dbg & 32);
 }
 
+// SPCL_SYM=0 switches the symmetric stats pass off (development A/B switch); so does debug flag 64
+static bool sym_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("SPCL_SYM");
+    env = (e == nullptr) ? 1 : (e[0] != '0');
+  }
+  return env != 0 && !(g_dbg & 64);
+}
+
 // minimax polynomials of 2^f on [-0.5, 0.5] (relative error 2.7e-6 / 7.5e-5)
 static const double kPoly4[5] = {0.999999261492568, 0.6931218184520522, 0.24024745066719647, 0.05591783074149139,
                                  0.00957007737459198};
@@ -1524,28 +1724,34 @@ extern "C" int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_p
 
   SPCL_CUDA_TRY(cudaMemsetAsync(acc + row_begin * 4, 0, static_cast<size_t>(row_end - row_begin) * 16, s));
 
-  // pass A: 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128
+  // pass A: 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128.
+  // A launch that owns every row (not a row shard) runs the symmetric variant: half the tiles.
   const bool wide = tc::pick_slots(p.dc, 256, false) >= 2 && !(tc::g_dbg & 16);
-  if (wide) {
+  const bool sym = row_begin == 0 && row_end == n_total && tc::sym_enabled();
+  {
+    const int bn = wide ? 256 : 128;
     tc::Params pa = p;
-    pa.CT = ceil_div(n_pad, 256);
-    pa.nslot = tc::pick_slots(p.dc, 256, false);
-    pa.nbuf = 2;
-    CUtensorMap tmap256;
-    rc = tc::make_zb_tensor_map(&tmap256, zb, n_pad, d_pad, 256);
+    pa.CT = ceil_div(n_pad, static_cast<int64_t>(bn));
+    pa.nslot = tc::pick_slots(p.dc, bn, false);
+    pa.nbuf = wide ? 2 : 4;
+    pa.sym = sym ? 1 : 0;
+    CUtensorMap tmapb = tmap128;
+    if (wide) {
+      rc = tc::make_zb_tensor_map(&tmapb, zb, n_pad, d_pad, 256);
+      if (rc != SPCL_OK) return rc;
+    }
+    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, bn, false) + 1024;
+    const int64_t total = sym ? tc::sym_prefix(pa.RB, pa.CT, bn) : pa.RB * pa.CT;
+    const unsigned grid = static_cast<unsigned>(total < tc::num_sms() ? total : tc::num_sms());
+    auto launch = [&](auto kernel) -> int {
+      const int r2 = tc::set_smem(kernel, smem);
+      if (r2 != SPCL_OK) return r2;
+      kernel<<<grid, tc::NTHREADS, smem, s>>>(tmap128, tmapb, pa);
+      return SPCL_OK;
+    };
+    if (wide) rc = sym ? launch(tc::stats_kernel<256, true>) : launch(tc::stats_kernel<256, false>);
+    else rc = sym ? launch(tc::stats_kernel<128, true>) : launch(tc::stats_kernel<128, false>);
     if (rc != SPCL_OK) return rc;
-    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, 256, false) + 1024;
-    rc = tc::set_smem(tc::stats_kernel<256>, smem);
-    if (rc != SPCL_OK) return rc;
-    tc::stats_kernel<256><<<tc::grid_for(pa), tc::NTHREADS, smem, s>>>(tmap128, tmap256, pa);
-  } else {
-    tc::Params pa = p;
-    pa.nslot = tc::pick_slots(p.dc, 128, false);
-    pa.nbuf = 4;
-    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, 128, false) + 1024;
-    rc = tc::set_smem(tc::stats_kernel<128>, smem);
-    if (rc != SPCL_OK) return rc;
-    tc::stats_kernel<128><<<tc::grid_for(pa), tc::NTHREADS, smem, s>>>(tmap128, tmap128, pa);
   }
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/stats");
 
