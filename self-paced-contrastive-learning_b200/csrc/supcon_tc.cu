@@ -172,8 +172,18 @@ __host__ __device__ inline int64_t sym_prefix(int64_t I, int64_t CT, int bn) {
   return bn == 2 * TILE ? I * CT - ((I - 1) * (I - 1)) / 4 : I * CT - (I * (I - 1)) / 2;
 }
 
+// Row blocks near the bottom of the triangle have only a few tiles, and every change of row block drains the
+// pipeline (new A tile), so the symmetric pass walks the row blocks in the folded order 0, RB-1, 1, RB-2, ...:
+// every CTA's contiguous range then covers about the same number of row blocks as well as of tiles.
+__host__ __device__ inline int64_t sym_fold(int64_t o, int64_t RB) { return (o & 1) ? RB - 1 - (o >> 1) : (o >> 1); }
+// tiles of the first o row blocks of the folded order
+__host__ __device__ inline int64_t sym_fold_prefix(int64_t o, int64_t RB, int64_t CT, int bn) {
+  const int64_t a = o >> 1;
+  return sym_prefix(a + (o & 1), CT, bn) + sym_prefix(RB, CT, bn) - sym_prefix(RB - a, CT, bn);
+}
+
 struct CtaRange {
-  int64_t I0;        // first row block (relative to row_begin)
+  int64_t I0;        // first row block (relative to row_begin); symmetric: its index in the folded order
   uint32_t t0, n;    // first column tile inside it, number of tiles
 };
 
@@ -189,13 +199,13 @@ __device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
   }
   const int64_t total = sym_prefix(p.RB, p.CT, bn);
   const int64_t f0 = total * blockIdx.x / gridDim.x, f1 = total * (blockIdx.x + 1) / gridDim.x;
-  int64_t lo = 0, hi = p.RB - 1;                 // largest I with sym_prefix(I) <= f0
+  int64_t lo = 0, hi = p.RB - 1;                 // largest o with sym_fold_prefix(o) <= f0
   while (lo < hi) {
     const int64_t mid = (lo + hi + 1) >> 1;
-    if (sym_prefix(mid, p.CT, bn) <= f0) lo = mid; else hi = mid - 1;
+    if (sym_fold_prefix(mid, p.RB, p.CT, bn) <= f0) lo = mid; else hi = mid - 1;
   }
   r.I0 = lo;
-  r.t0 = static_cast<uint32_t>(sym_first_tile(lo, bn) + (f0 - sym_prefix(lo, p.CT, bn)));
+  r.t0 = static_cast<uint32_t>(sym_first_tile(sym_fold(lo, p.RB), bn) + (f0 - sym_fold_prefix(lo, p.RB, p.CT, bn)));
   r.n = static_cast<uint32_t>(f1 - f0);
   return r;
 }
@@ -203,15 +213,21 @@ __device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
 // Walks the CTA's flattened tile range one tile at a time; a "segment" is the part of one row block.
 // 32-bit state: the per-tile bookkeeping of the single-thread roles sits on the critical path.
 struct TileCursor {
-  uint32_t t, CT, it, n, seg, tfirst, I;
+  uint32_t t, CT, it, n, seg, tfirst;
+  uint32_t I;        // current row block (relative to row_begin)
+  uint32_t o, RB;    // symmetric: position in the folded order, number of row blocks
   int symshift;      // < 0: every row block starts at tile 0; else row block I starts at tile I >> symshift
   __device__ __forceinline__ TileCursor(int64_t f0, int64_t f1, int64_t ct)
       : t(static_cast<uint32_t>(f0 % ct)), CT(static_cast<uint32_t>(ct)), it(0), n(static_cast<uint32_t>(f1 - f0)),
-        seg(0), tfirst(0), I(0), symshift(-1) {}
-  __device__ __forceinline__ TileCursor(const CtaRange& r, int64_t ct, int symshift_)
-      : t(r.t0), CT(static_cast<uint32_t>(ct)), it(0), n(r.n), seg(0),
-        tfirst(symshift_ >= 0 ? static_cast<uint32_t>(r.I0) >> symshift_ : 0u), I(static_cast<uint32_t>(r.I0)),
-        symshift(symshift_) {}
+        seg(0), tfirst(0), I(static_cast<uint32_t>(f0 / ct)), o(0), RB(0), symshift(-1) {}
+  __device__ __forceinline__ TileCursor(const CtaRange& r, int64_t ct, int64_t rb, int symshift_)
+      : t(r.t0), CT(static_cast<uint32_t>(ct)), it(0), n(r.n), seg(0), tfirst(0), I(static_cast<uint32_t>(r.I0)),
+        o(static_cast<uint32_t>(r.I0)), RB(static_cast<uint32_t>(rb)), symshift(symshift_) {
+    if (symshift >= 0) {
+      I = static_cast<uint32_t>(sym_fold(o, RB));
+      tfirst = I >> symshift;
+    }
+  }
   __device__ __forceinline__ bool valid() const { return it < n; }
   __device__ __forceinline__ bool first() const { return it == 0 || t == tfirst; }
   __device__ __forceinline__ bool last() const { return it + 1 == n || t + 1 == CT; }
@@ -219,8 +235,13 @@ struct TileCursor {
     if (last()) ++seg;
     ++it;
     if (++t == CT) {
-      ++I;
-      tfirst = symshift >= 0 ? I >> symshift : 0u;
+      if (symshift >= 0) {
+        ++o;
+        I = (o & 1u) ? RB - 1u - (o >> 1) : (o >> 1);
+        tfirst = I >> symshift;
+      } else {
+        ++I;
+      }
       t = tfirst;
     }
   }
@@ -395,41 +416,54 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// fast: every element is a valid negative.  lo / hi are the 16x256b fragments (ptx::tmem_ld_16x256b_x4) of lanes
-// [0, 16) / [16, 32) of the warp's TMEM quadrant for 32 columns: this thread holds rows 16 h + 8 k + lane / 4 and
-// columns 8 r + 2 (lane % 4) + {0, 1}.  racc[2 h + k] += E (row partials, two columns per instruction); returns
-// the sum over the warp's 32 rows for column  16 b4 + 8 b3 + 2 (lane % 4) + b2  (b_i = bit i of lane): four adds
-// per column in the thread, then a 3-step butterfly over the 8 threads that share the column (7 shuffles).
-__device__ __forceinline__ float stats_chunk_sym(const uint32_t (&lo)[16], const uint32_t (&hi)[16], const ExpK& k,
-                                                 uint64_t (&racc)[4], int lane) {
-  uint64_t col[4];
+// fast: every element is a valid negative.  v = one 16x256b fragment (ptx::tmem_ld_16x256b_x4) of lanes
+// [16 H, 16 H + 16) of the warp's TMEM quadrant for 32 columns: this thread holds rows 16 H + 8 k + lane / 4 and
+// columns 8 r + 2 (lane % 4) + {0, 1}.  racc[2 H + k] += E (row partials, two columns per instruction);
+// col[r] (+)= this thread's partial sums (over its rows) of column pair r.
+template <int H>
+__device__ __forceinline__ void stats_half_sym(const uint32_t (&v)[16], const ExpK& k, uint64_t (&racc)[4],
+                                               uint64_t (&col)[4]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    uint64_t e[4];
-#pragma unroll
-    for (int hk = 0; hk < 4; ++hk) {
-      const int i = 4 * r + 2 * (hk & 1);
-      const uint64_t d2 = (hk & 2) ? pack_u32x2(hi[i], hi[i + 1]) : pack_u32x2(lo[i], lo[i + 1]);
-      e[hk] = use_poly(4 * r + hk, SPCL_FWD_POLY_PAIRS) ? ex2_poly2<4>(d2, k) : ex2_mufu2(d2, k);
-      racc[hk] = add_f32x2(racc[hk], e[hk]);
-    }
-    col[r] = add_f32x2(add_f32x2(e[0], e[1]), add_f32x2(e[2], e[3]));
+    const uint64_t e0 = use_poly(4 * r + 2 * H, SPCL_FWD_POLY_PAIRS) ? ex2_poly2<4>(pack_u32x2(v[4 * r], v[4 * r + 1]), k)
+                                                                     : ex2_mufu2(pack_u32x2(v[4 * r], v[4 * r + 1]), k);
+    const uint64_t e1 = use_poly(4 * r + 2 * H + 1, SPCL_FWD_POLY_PAIRS)
+                            ? ex2_poly2<4>(pack_u32x2(v[4 * r + 2], v[4 * r + 3]), k)
+                            : ex2_mufu2(pack_u32x2(v[4 * r + 2], v[4 * r + 3]), k);
+    racc[2 * H] = add_f32x2(racc[2 * H], e0);
+    racc[2 * H + 1] = add_f32x2(racc[2 * H + 1], e1);
+    const uint64_t c = add_f32x2(e0, e1);
+    col[r] = (H == 0) ? c : add_f32x2(col[r], c);
   }
-  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-  // xor 16: keep column groups r = 2 b4 + {0, 1}
-  uint64_t k0 = b4 ? col[2] : col[0], k1 = b4 ? col[3] : col[1];
-  const uint64_t s0 = b4 ? col[0] : col[2], s1 = b4 ? col[1] : col[3];
-  k0 = add_f32x2(k0, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(s0), 16));
-  k1 = add_f32x2(k1, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(s1), 16));
-  // xor 8: keep r = 2 b4 + b3
-  uint64_t kk = b3 ? k1 : k0;
-  const uint64_t ss = b3 ? k0 : k1;
-  kk = add_f32x2(kk, __shfl_xor_sync(kFullMask, static_cast<unsigned long long>(ss), 8));
-  // xor 4: keep c = b2
-  float c0, c1;
-  unpack_f32x2(kk, c0, c1);
-  const float kf = b2 ? c1 : c0, sf = b2 ? c0 : c1;
-  return kf + __shfl_xor_sync(kFullMask, sf, 4);
+}
+
+// Column sums of a 128-column block over the warp's 32 rows: a 3-step butterfly over the 8 threads that share a
+// column (lane bits 4, 3, 2).  Step 1 runs per 32-column chunk (it halves the live partials), steps 2 and 3 for
+// the four chunks together so the shuffle latencies overlap.  A lane ends with column
+// 16 b4 + 8 b3 + 2 (lane % 4) + b2 of every chunk and adds it to that anchor's rowsum (colacc = &acc[j0 + that
+// column].x, acc is float4 per anchor).
+__device__ __forceinline__ void sym_col_step1(const uint64_t (&col)[4], uint64_t& k0, uint64_t& k1, int lane) {
+  const bool b4 = (lane & 16) != 0;                // xor 16: keep column pairs r = 2 b4 + {0, 1}
+  const unsigned long long s0 = b4 ? col[0] : col[2], s1 = b4 ? col[1] : col[3];
+  k0 = add_f32x2(b4 ? col[2] : col[0], __shfl_xor_sync(kFullMask, s0, 16));
+  k1 = add_f32x2(b4 ? col[3] : col[1], __shfl_xor_sync(kFullMask, s1, 16));
+}
+__device__ __forceinline__ void sym_col_flush(uint64_t (&k0)[4], const uint64_t (&k1)[4], float* colacc, int lane) {
+  const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {                 // xor 8: keep r = 2 b4 + b3
+    const unsigned long long ss = b3 ? k0[ch] : k1[ch];
+    k0[ch] = add_f32x2(b3 ? k1[ch] : k0[ch], __shfl_xor_sync(kFullMask, ss, 8));
+  }
+  float out[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {                 // xor 4: keep column b2 of the pair
+    float c0, c1;
+    unpack_f32x2(k0[ch], c0, c1);
+    out[ch] = (b2 ? c1 : c0) + __shfl_xor_sync(kFullMask, b2 ? c0 : c1, 4);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) atomicAdd(colacc + ch * 32 * 4, out[ch]);
 }
 
 // slow + column sums (tiles right of the diagonal that may hold positives, tail block): 32x32b layout, this
@@ -567,7 +601,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
 
   const CtaRange range = cta_range_of(p, BN);
   constexpr int kSymShift = SYM ? (kSub == 2 ? 1 : 0) : -1;
-  const int64_t rb0 = p.row_begin / TILE, I0 = range.I0;
+  const int64_t rb0 = p.row_begin / TILE;
   const uint32_t a_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
   const uint32_t slot_tx = static_cast<uint32_t>(p.dc) * BN * 128;
 
@@ -575,9 +609,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       Ring rs(p.nslot);
-      for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rs.next()) {
+      for (TileCursor c(range, p.CT, p.RB, kSymShift); c.valid(); c.next(), rs.next()) {
         if (c.first()) {
-          const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
+          const int32_t gi0 = static_cast<int32_t>(p.row_begin + static_cast<int64_t>(c.I) * TILE);
           mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
           mbar_arrive_expect_tx(&bar->a_full, a_tx);
           for (int k = 0; k < p.dc; ++k) tma_load_2d(sm.a_tile + k * CHUNK_BYTES, &tmap_a, &bar->a_full, k * 64, gi0);
@@ -610,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     const uint32_t a_base = smem_u32(sm.a_tile);
     const int nk = p.dc * 4;
     Ring rs(p.nslot), rb(kBufs);
-    for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rs.next(), rb.next()) {
+    for (TileCursor c(range, p.CT, p.RB, kSymShift); c.valid(); c.next(), rs.next(), rb.next()) {
       if ((c.it & 1) != mw) continue;
       if (lane == 0) {
         if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
@@ -666,14 +700,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
     };
     uint32_t mask = 0, mask_grp = 0xffffffffu;
     Ring rb(kBufs);
-    for (TileCursor c(range, p.CT, kSymShift); c.valid(); c.next(), rb.next()) {
+    for (TileCursor c(range, p.CT, p.RB, kSymShift); c.valid(); c.next(), rb.next()) {
       if (c.first()) {
-        gi0 = p.row_begin + (I0 + c.seg) * TILE;
+        gi0 = p.row_begin + static_cast<int64_t>(c.I) * TILE;
         gi = gi0 + r;
         row_jb = static_cast<uint32_t>(gi0 / TILE);
         row_ok = gi < p.row_end;
         li = row_ok ? p.labels[gi] : 0;
-        rsig = p.sig[rb0 + I0 + c.seg];
+        rsig = p.sig[rb0 + c.I];
         mask_grp = 0xffffffffu;
       }
       const bool mine = (kSub == 2) || (static_cast<int>(c.it & 1) == wg);
@@ -696,25 +730,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
           const uint32_t taddr = lane_base + buf * BN + (kSub == 2 ? wg * TILE : 0);
           if (SYM && cols && !slow) {
             // fragment loads of the two 16-lane halves, double buffered like the row layout below
-            uint32_t la[16], ha[16], lb[16], hb[16];
-            float* colacc = reinterpret_cast<float*>(p.acc + j0 + sym_col);
-            tmem_ld_16x256b_x4(taddr, la);
-            tmem_ld_16x256b_x4(taddr + (16u << 16), ha);
+            uint32_t fa[16], fb[16];                 // fa: lanes [0, 16) of the quadrant, fb: lanes [16, 32)
+            uint64_t col[4], k0[4], k1[4];
+            tmem_ld_16x256b_x4(taddr, fa);
             tmem_wait_ld();
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-              uint32_t(&cl)[16] = (ch & 1) ? lb : la;
-              uint32_t(&chh)[16] = (ch & 1) ? hb : ha;
-              uint32_t(&nl)[16] = (ch & 1) ? la : lb;
-              uint32_t(&nh)[16] = (ch & 1) ? ha : hb;
-              if (ch < 3) {
-                tmem_ld_16x256b_x4(taddr + (ch + 1) * 32, nl);
-                tmem_ld_16x256b_x4(taddr + (16u << 16) + (ch + 1) * 32, nh);
-              }
-              const float cs = stats_chunk_sym(cl, chh, ek, acc2, lane);
-              atomicAdd(colacc + ch * 32 * 4, cs);               // acc is float4 per anchor: .x = rowsum
+              tmem_ld_16x256b_x4(taddr + (16u << 16) + ch * 32, fb);         // in flight during the math below
+              if (p.dbg & 1) acc2[ch] ^= fa[ch];
+              else stats_half_sym<0>(fa, ek, acc2, col);
+              tmem_wait_ld();
+              if (ch < 3) tmem_ld_16x256b_x4(taddr + (ch + 1) * 32, fa);
+              if (p.dbg & 1) acc2[ch] ^= fb[ch];
+              else stats_half_sym<1>(fb, ek, acc2, col);
               if (ch < 3) tmem_wait_ld();
+              sym_col_step1(col, k0[ch], k1[ch], lane);
             }
+            if (!(p.dbg & 1)) sym_col_flush(k0, k1, reinterpret_cast<float*>(p.acc + j0 + sym_col), lane);
           } else {
             const int64_t dj = gi - j0;
             const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
