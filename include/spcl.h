@@ -101,6 +101,22 @@ int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t
                          const int32_t* sig, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
                          int mode, float* acc, float* row_stats, float* partials, spcl_stream_t stream);
 
+/* ---- the same forward in two steps, for row sharding -------------------------------------------
+ * S, exp(S) and the label masks are symmetric, so pass A (contrast_loss3.py:25-31,:157-167,:180-182) needs only
+ * the tiles on or right of the diagonal: a tile gives the sums over its rows AND over its columns.
+ * spcl_supcon_stats_part_bf16 runs share `part` of `nparts` equal shares of that triangle over the gathered
+ * operands (any rows, not this rank's) and ADDS into acc (float [n_pad][4], zeroed by the caller); the
+ * caller then sums acc over the ranks (all-reduce).  spcl_supcon_fwd_finish_bf16 takes the complete acc and
+ * does the rest of spcl_supcon_fwd_bf16 for the owned rows (self-paced pass :184-197,:207-214, row_stats,
+ * partials).  nparts == 1 followed by finish over all rows equals spcl_supcon_fwd_bf16. */
+int spcl_supcon_stats_part_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
+                                const int32_t* labels, const int32_t* sig, int32_t part, int32_t nparts,
+                                float inv_tau, int mode, float* acc, spcl_stream_t stream);
+int spcl_supcon_fwd_finish_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
+                                const int32_t* labels, const int32_t* sig, int64_t row_begin, int64_t row_end,
+                                float inv_tau, float gamma, int mode, float* acc, float* row_stats,
+                                float* partials, spcl_stream_t stream);
+
 /* ---- fused backward, tensor-core path --------------------------------------------------------
  * row_stats must hold ALL N rows (all-gathered when sharded).  dz: float [row_end-row_begin][lddz],
  * zeroed by the call; dz_i = grad_out * scale / (N tau) * sum_j T_ij z_j.  Replaces autograd of

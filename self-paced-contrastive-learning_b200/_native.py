@@ -32,6 +32,9 @@ SIGNATURES = {
     "spcl_supcon_prepare_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr],
     "spcl_supcon_fwd_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
                              _ptr, _ptr],
+    "spcl_supcon_stats_part_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i32, _i32, _f32, _c.c_int, _ptr, _ptr],
+    "spcl_supcon_fwd_finish_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
+                                    _ptr, _ptr],
     "spcl_supcon_bwd_bf16": [_ptr, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _f32,
                              _c.c_int, _ptr, _i64, _ptr],
     "spcl_supcon_fwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _c.c_int, _ptr,

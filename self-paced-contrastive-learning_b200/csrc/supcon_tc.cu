@@ -87,6 +87,9 @@ struct Params {
   unsigned long long* trace;   // debug timeline (CTA 0), normally nullptr
   int dbg;                     // debug experiment switches (tools/gpu_exp.py), normally 0
   int sym;                     // stats pass visits only tiles on / right of the diagonal block (square launches)
+  // symmetric pass split over ranks: this launch is CTAs [vblock0, vblock0 + gridDim.x) of a virtual grid of
+  // vgrid CTAs that together cover the triangle (vgrid == 0: the launch is the whole grid)
+  unsigned vgrid, vblock0;
 };
 
 // debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
@@ -198,7 +201,8 @@ __device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
     return r;
   }
   const int64_t total = sym_prefix(p.RB, p.CT, bn);
-  const int64_t f0 = total * blockIdx.x / gridDim.x, f1 = total * (blockIdx.x + 1) / gridDim.x;
+  const int64_t vb = p.vgrid ? p.vblock0 + blockIdx.x : blockIdx.x, vg = p.vgrid ? p.vgrid : gridDim.x;
+  const int64_t f0 = total * vb / vg, f1 = total * (vb + 1) / vg;
   int64_t lo = 0, hi = p.RB - 1;                 // largest o with sym_fold_prefix(o) <= f0
   while (lo < hi) {
     const int64_t mid = (lo + hi + 1) >> 1;
@@ -1738,55 +1742,49 @@ static int max_pair_clusters(size_t smem_bytes) {
 
 using namespace spcl;
 
-extern "C" int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
-                                    const int32_t* labels, const int32_t* sig, int64_t row_begin, int64_t row_end,
-                                    float inv_tau, float gamma, int mode, float* acc, float* row_stats,
-                                    float* partials, spcl_stream_t stream) {
-  tc::Params p{};
-  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
-  if (rc != SPCL_OK) return rc;
-  if (zb == nullptr || acc == nullptr || row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
-  if ((reinterpret_cast<uintptr_t>(zb) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15))
-    return SPCL_ERR_INVALID_ARG;
-  p.acc = reinterpret_cast<float4*>(acc);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUtensorMap tmap128;
-  rc = tc::make_zb_tensor_map(&tmap128, zb, n_pad, d_pad, tc::TILE);
-  if (rc != SPCL_OK) return rc;
-
-  SPCL_CUDA_TRY(cudaMemsetAsync(acc + row_begin * 4, 0, static_cast<size_t>(row_end - row_begin) * 16, s));
-
-  // pass A: 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128.
-  // A launch that owns every row (not a row shard) runs the symmetric variant: half the tiles.
+// pass A launcher.  part / nparts: share of the symmetric triangle (nparts == 1: the whole launch; sym == false:
+// the rectangular rows x all-columns pass of a row shard).
+static int launch_stats(const tc::Params& p, const void* zb, int64_t n_pad, int32_t d_pad, bool sym, int part,
+                        int nparts, const CUtensorMap& tmap128, cudaStream_t s) {
+  // 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128
   const bool wide = tc::pick_slots(p.dc, 256, false) >= 2 && !(tc::g_dbg & 16);
-  const bool sym = row_begin == 0 && row_end == n_total && tc::sym_enabled();
-  {
-    const int bn = wide ? 256 : 128;
-    tc::Params pa = p;
-    pa.CT = ceil_div(n_pad, static_cast<int64_t>(bn));
-    pa.nslot = tc::pick_slots(p.dc, bn, false);
-    pa.nbuf = wide ? 2 : 4;
-    pa.sym = sym ? 1 : 0;
-    CUtensorMap tmapb = tmap128;
-    if (wide) {
-      rc = tc::make_zb_tensor_map(&tmapb, zb, n_pad, d_pad, 256);
-      if (rc != SPCL_OK) return rc;
-    }
-    const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, bn, false) + 1024;
-    const int64_t total = sym ? tc::sym_prefix(pa.RB, pa.CT, bn) : pa.RB * pa.CT;
-    const unsigned grid = static_cast<unsigned>(total < tc::num_sms() ? total : tc::num_sms());
-    auto launch = [&](auto kernel) -> int {
-      const int r2 = tc::set_smem(kernel, smem);
-      if (r2 != SPCL_OK) return r2;
-      kernel<<<grid, tc::NTHREADS, smem, s>>>(tmap128, tmapb, pa);
-      return SPCL_OK;
-    };
-    if (wide) rc = sym ? launch(tc::stats_kernel<256, true>) : launch(tc::stats_kernel<256, false>);
-    else rc = sym ? launch(tc::stats_kernel<128, true>) : launch(tc::stats_kernel<128, false>);
+  const int bn = wide ? 256 : 128;
+  tc::Params pa = p;
+  pa.CT = ceil_div(n_pad, static_cast<int64_t>(bn));
+  pa.nslot = tc::pick_slots(p.dc, bn, false);
+  pa.nbuf = wide ? 2 : 4;
+  pa.sym = sym ? 1 : 0;
+  CUtensorMap tmapb = tmap128;
+  int rc = SPCL_OK;
+  if (wide) {
+    rc = tc::make_zb_tensor_map(&tmapb, zb, n_pad, d_pad, 256);
     if (rc != SPCL_OK) return rc;
   }
+  const size_t smem = tc::smem_payload_bytes(pa.dc, pa.nslot, bn, false) + 1024;
+  const int64_t total = sym ? tc::sym_prefix(pa.RB, pa.CT, bn) : pa.RB * pa.CT;
+  const int64_t share = ceil_div(total, static_cast<int64_t>(nparts));
+  const unsigned grid = static_cast<unsigned>(share < tc::num_sms() ? share : tc::num_sms());
+  if (nparts > 1) {
+    pa.vgrid = grid * static_cast<unsigned>(nparts);
+    pa.vblock0 = grid * static_cast<unsigned>(part);
+  }
+  auto launch = [&](auto kernel) -> int {
+    const int r2 = tc::set_smem(kernel, smem);
+    if (r2 != SPCL_OK) return r2;
+    kernel<<<grid, tc::NTHREADS, smem, s>>>(tmap128, tmapb, pa);
+    return SPCL_OK;
+  };
+  if (wide) rc = sym ? launch(tc::stats_kernel<256, true>) : launch(tc::stats_kernel<256, false>);
+  else rc = sym ? launch(tc::stats_kernel<128, true>) : launch(tc::stats_kernel<128, false>);
+  if (rc != SPCL_OK) return rc;
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/stats");
+  return SPCL_OK;
+}
 
+// pass B (self-paced sums over the positive tiles) + per-row finalisation, from complete pass A sums in acc
+static int launch_finish(const tc::Params& p, int64_t n_pad, int64_t row_begin, int64_t row_end, float inv_tau,
+                         int mode, float* row_stats, float* partials, const CUtensorMap& tmap128, cudaStream_t s) {
+  int rc = SPCL_OK;
   if (mode != SPCL_MODE_NONE) {
     tc::Params pb = p;
     pb.nslot = tc::pick_slots(p.dc, 128, true);
@@ -1802,6 +1800,74 @@ extern "C" int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_p
                                                 partials);
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/row_finalize");
   return SPCL_OK;
+}
+
+static int check_fwd_args(const void* zb, const int32_t* labels, const float* acc) {
+  if (zb == nullptr || acc == nullptr) return SPCL_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(zb) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15)) return SPCL_ERR_INVALID_ARG;
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_fwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
+                                    const int32_t* labels, const int32_t* sig, int64_t row_begin, int64_t row_end,
+                                    float inv_tau, float gamma, int mode, float* acc, float* row_stats,
+                                    float* partials, spcl_stream_t stream) {
+  tc::Params p{};
+  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
+  rc = check_fwd_args(zb, labels, acc);
+  if (rc != SPCL_OK) return rc;
+  p.acc = reinterpret_cast<float4*>(acc);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmap128;
+  rc = tc::make_zb_tensor_map(&tmap128, zb, n_pad, d_pad, tc::TILE);
+  if (rc != SPCL_OK) return rc;
+  // A launch that owns every row (not a row shard) runs the symmetric pass A: half the tiles.
+  const bool sym = row_begin == 0 && row_end == n_total && tc::sym_enabled();
+  if (sym) {
+    SPCL_CUDA_TRY(cudaMemsetAsync(acc, 0, static_cast<size_t>(n_pad) * 16, s));   // column sums reach padded rows
+  } else {
+    SPCL_CUDA_TRY(cudaMemsetAsync(acc + row_begin * 4, 0, static_cast<size_t>(row_end - row_begin) * 16, s));
+  }
+  rc = launch_stats(p, zb, n_pad, d_pad, sym, 0, 1, tmap128, s);
+  if (rc != SPCL_OK) return rc;
+  return launch_finish(p, n_pad, row_begin, row_end, inv_tau, mode, row_stats, partials, tmap128, s);
+}
+
+extern "C" int spcl_supcon_stats_part_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
+                                           const int32_t* labels, const int32_t* sig, int32_t part, int32_t nparts,
+                                           float inv_tau, int mode, float* acc, spcl_stream_t stream) {
+  if (nparts < 1 || part < 0 || part >= nparts) return SPCL_ERR_INVALID_ARG;
+  tc::Params p{};
+  // gamma plays no role in pass A; hard / soft only decide whether sum P <z_i, z_j> is collected
+  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, 0, n_total, inv_tau, 1.f, mode);
+  if (rc != SPCL_OK) return rc;
+  rc = check_fwd_args(zb, labels, acc);
+  if (rc != SPCL_OK) return rc;
+  p.acc = reinterpret_cast<float4*>(acc);
+  CUtensorMap tmap128;
+  rc = tc::make_zb_tensor_map(&tmap128, zb, n_pad, d_pad, tc::TILE);
+  if (rc != SPCL_OK) return rc;
+  return launch_stats(p, zb, n_pad, d_pad, true, part, nparts, tmap128, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int spcl_supcon_fwd_finish_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad,
+                                           const int32_t* labels, const int32_t* sig, int64_t row_begin,
+                                           int64_t row_end, float inv_tau, float gamma, int mode, float* acc,
+                                           float* row_stats, float* partials, spcl_stream_t stream) {
+  tc::Params p{};
+  int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || partials == nullptr) return SPCL_ERR_INVALID_ARG;
+  rc = check_fwd_args(zb, labels, acc);
+  if (rc != SPCL_OK) return rc;
+  p.acc = reinterpret_cast<float4*>(acc);      // pass B adds its two sums to .z / .w
+  CUtensorMap tmap128;
+  rc = tc::make_zb_tensor_map(&tmap128, zb, n_pad, d_pad, tc::TILE);
+  if (rc != SPCL_OK) return rc;
+  return launch_finish(p, n_pad, row_begin, row_end, inv_tau, mode, row_stats, partials, tmap128,
+                       static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad, int32_t d,

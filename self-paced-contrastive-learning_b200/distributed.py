@@ -4,8 +4,11 @@ The reference is single-process; this is additive.  Every rank holds the two vie
 samples (``z1``, ``z2``: ``[n_loc, d]``) and owns the anchor rows of those samples against ALL
 columns:
 
-  forward : pack local operands -> all-gather Z (bf16) and the labels -> fused forward on the owned
-            rows -> all-reduce of the three partial sums -> loss / ratio / scale on every rank;
+  forward : pack local operands -> all-gather Z (bf16) and the labels -> pass A (row sums of exp(S), positive
+            counts): the tile triangle on / right of the diagonal is cut into `world` equal shares, every
+            rank runs one share (S is symmetric: a tile yields its row AND column sums) and the sums are
+            all-reduced (16 B per anchor) -> self-paced pass + row statistics on the owned rows ->
+            all-reduce of the three partial sums -> loss / ratio / scale on every rank;
             all-gather of the per-row statistics for the backward.
   backward: fused backward on the owned rows.  T = dS + dS^T is formed per tile from both blocks'
             statistics, so each rank ends with exactly the gradient rows of its own embeddings:
@@ -64,17 +67,29 @@ class NativeBackend:
                  _stream(z1))
         return out
 
-    def forward_rows(self, z_all, labels_all, plan: ShardPlan, inv_tau, gamma, mode):
+    #: pass A of a shard = this rank's share of the symmetric tile triangle + an all-reduce of the row sums
+    #: (half the tiles of the rows x all-columns rectangle); False keeps the rectangular pass (A/B switch)
+    symmetric = True
+
+    def forward_rows(self, z_all, labels_all, plan: ShardPlan, inv_tau, gamma, mode, group=None):
         N, d_pad = z_all.shape
         dev = z_all.device
         st = _stream(z_all)
         sig = torch.empty(N // nat.TILE, 4, dtype=torch.int32, device=dev)
         nat.call("spcl_label_block_sig", _ptr(labels_all), N, N, _ptr(sig), st)
-        acc = torch.empty(N, 4, dtype=torch.float32, device=dev)
         row_stats = torch.zeros(4, N, dtype=torch.float32, device=dev)
         partials = torch.zeros(3, dtype=torch.float32, device=dev)
-        nat.call("spcl_supcon_fwd_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig), plan.row_begin,
-                 plan.row_end, inv_tau, gamma, mode, _ptr(acc), _ptr(row_stats), _ptr(partials), st)
+        if self.symmetric and plan.world > 1:
+            acc = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+            nat.call("spcl_supcon_stats_part_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig), plan.rank,
+                     plan.world, inv_tau, mode, _ptr(acc), st)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)          # 16 B per anchor
+            nat.call("spcl_supcon_fwd_finish_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig),
+                     plan.row_begin, plan.row_end, inv_tau, gamma, mode, _ptr(acc), _ptr(row_stats), _ptr(partials), st)
+        else:
+            acc = torch.empty(N, 4, dtype=torch.float32, device=dev)
+            nat.call("spcl_supcon_fwd_bf16", _ptr(z_all), N, N, d_pad, _ptr(labels_all), _ptr(sig), plan.row_begin,
+                     plan.row_end, inv_tau, gamma, mode, _ptr(acc), _ptr(row_stats), _ptr(partials), st)
         return row_stats[:, plan.row_begin:plan.row_end].contiguous(), partials, sig
 
     def finalize(self, partials, N, correct_grad):
@@ -109,7 +124,7 @@ class _ShardedSupCon(torch.autograd.Function):
         z_loc = backend.pack(z1.contiguous(), z2.contiguous())
         z_all = _gather_rows(z_loc, world, group)                       # N * d_pad * 2 B over NVLink
         labels_all = _gather_rows(torch.cat([labels, labels]), world, group)
-        stats_loc, partials, sig = backend.forward_rows(z_all, labels_all, plan, inv_tau, float(gamma), int(mode))
+        stats_loc, partials, sig = backend.forward_rows(z_all, labels_all, plan, inv_tau, float(gamma), int(mode), group)
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)    # 3 floats
         scalars = backend.finalize(partials, plan.N, bool(correct_grad))
         # 16 B per anchor; ranks contribute [4, rows_loc] plane slices -> [4, N] planes

@@ -32,7 +32,7 @@ class OracleBackend:
         return supcon_closed_form(z[: N // 2], z[N // 2:], anchor_labels=labels_all.numpy(), temperature=1.0 / inv_tau,
                                   gamma=gamma, mode={0: "none", 1: "hard", 2: "soft"}[mode], **kw)
 
-    def forward_rows(self, z_all, labels_all, plan, inv_tau, gamma, mode):
+    def forward_rows(self, z_all, labels_all, plan, inv_tau, gamma, mode, group=None):
         r = self._full(z_all, labels_all, inv_tau, gamma, mode, want_grad=False,
                        row_range=(plan.row_begin, plan.row_end))
         sl = slice(plan.row_begin, plan.row_end)

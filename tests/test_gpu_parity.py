@@ -396,3 +396,56 @@ def test_hostfeed_matches_direct_calls():
     with pytest.raises(RuntimeError):
         for _ in range(3):
             feed.push(*pinned[0], lab_h)
+
+
+# ---- symmetric pass A: split API == one call == rectangular pass --------------------------------
+@pytest.mark.parametrize("n,d,kind,mode", [(1000, 128, "patient", "none"), (1000, 128, "partition", "soft"),
+                                           (331, 256, "cycle", "soft"), (2048, 64, "self", "soft")])
+@pytest.mark.parametrize("nparts", [1, 3])
+def test_stats_parts_plus_finish_equals_fused_forward(n, d, kind, mode, nparts):
+    """spcl_supcon_stats_part_bf16 x nparts (+ sum) + spcl_supcon_fwd_finish_bf16 == spcl_supcon_fwd_bf16, and the
+    symmetric whole-launch pass == the rectangular pass a row shard runs (two row ranges)."""
+    from spcl_b200.ops import _ptr, _stream, pad_to
+    labels = torch.arange(n).int() if kind == "self" else acdc_meta_labels(n)[kind].int()
+    z1, z2 = make_views(labels, d, sigma=0.7, seed=3)
+    z1, z2, lab = z1.cuda(), z2.cuda(), labels.cuda()
+    N, n_pad, d_pad = 2 * n, pad_to(2 * n, nat.TILE), pad_to(d, 64)
+    dev = z1.device
+    st = _stream(z1)
+    zpack = torch.empty(n_pad, d_pad, dtype=torch.bfloat16, device=dev)
+    labels_full = torch.empty(n_pad, dtype=torch.int32, device=dev)
+    sig = torch.empty(n_pad // nat.TILE, 4, dtype=torch.int32, device=dev)
+    scratch = torch.empty(3, dtype=torch.float32, device=dev)
+    nat.call("spcl_supcon_prepare_bf16", _ptr(z1), _ptr(z2), n, d, z1.stride(0), z2.stride(0), _ptr(lab),
+             _ptr(zpack), n_pad, d_pad, _ptr(labels_full), _ptr(sig), _ptr(scratch), st)
+    inv_tau, gamma, m = 1.0 / 0.07, 6.0, MODE[mode]
+
+    def fused(ranges):
+        acc = torch.empty(n_pad, 4, dtype=torch.float32, device=dev)
+        rs = torch.zeros(4, n_pad, dtype=torch.float32, device=dev)
+        pt = torch.zeros(3, dtype=torch.float32, device=dev)
+        for rb, re in ranges:
+            nat.call("spcl_supcon_fwd_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), rb, re,
+                     inv_tau, gamma, m, _ptr(acc), _ptr(rs), _ptr(pt), st)
+        return rs[:, :N].cpu().numpy().astype(np.float64), pt.cpu().numpy().astype(np.float64)
+
+    rs_one, pt_one = fused([(0, N)])                                  # symmetric pass
+    cut = 128 * max(1, (N // 128) // 3)
+    rs_rect, pt_rect = fused([(0, cut), (cut, N)])                    # two row shards: rectangular pass
+
+    acc = torch.zeros(n_pad, 4, dtype=torch.float32, device=dev)
+    for part in range(nparts):                                        # what the ranks do, then all-reduce
+        nat.call("spcl_supcon_stats_part_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), part,
+                 nparts, inv_tau, m, _ptr(acc), st)
+    rs = torch.zeros(4, n_pad, dtype=torch.float32, device=dev)
+    pt = torch.zeros(3, dtype=torch.float32, device=dev)
+    nat.call("spcl_supcon_fwd_finish_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), 0, N,
+             inv_tau, gamma, m, _ptr(acc), _ptr(rs), _ptr(pt), st)
+    rs_split, pt_split = rs[:, :N].cpu().numpy().astype(np.float64), pt.cpu().numpy().astype(np.float64)
+
+    for other_rs, other_pt in ((rs_rect, pt_rect), (rs_split, pt_split)):
+        np.testing.assert_array_equal(other_rs[1], rs_one[1])                      # 1 / c_i: counts are exact
+        np.testing.assert_allclose(other_rs[0], rs_one[0], rtol=0, atol=2e-5)      # logD: summation order only
+        np.testing.assert_allclose(other_rs[2], rs_one[2], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(other_rs[3], rs_one[3], rtol=1e-4)
+        np.testing.assert_allclose(other_pt, pt_one, rtol=2e-5)
