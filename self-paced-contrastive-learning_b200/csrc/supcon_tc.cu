@@ -58,10 +58,10 @@ constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp =
 
 // pairs (of the 16 per 32-column chunk) whose exponential runs on the FMA pipe
 #ifndef SPCL_FWD_POLY_PAIRS
-#define SPCL_FWD_POLY_PAIRS 7
+#define SPCL_FWD_POLY_PAIRS 5
 #endif
 #ifndef SPCL_BWD_POLY_PAIRS
-#define SPCL_BWD_POLY_PAIRS 5
+#define SPCL_BWD_POLY_PAIRS 3
 #endif
 
 struct Params {

@@ -17,6 +17,9 @@ METRICS = [
     "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sectors_op_read.sum", "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
 ]
 
 
@@ -40,7 +43,7 @@ def full(tag, which):
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
-    out = [f"# ncu --set full --clock-control none --import-source on -k regex:{which}_kernel  ({rep.name})"]
+    out = [f"# ncu --set full --clock-control none --import-source on -k regex:{"stats" if which == "fwd" else which}_kernel  ({rep.name})"]
     for r in rows[2:]:
         out.append(f"## {r[hdr.index('Kernel Name')]}")
         for m in METRICS:
