@@ -452,7 +452,8 @@ __device__ __forceinline__ void sym_col_step1(const uint64_t (&col)[4], uint64_t
   k0 = add_f32x2(b4 ? col[2] : col[0], __shfl_xor_sync(kFullMask, s0, 16));
   k1 = add_f32x2(b4 ? col[3] : col[1], __shfl_xor_sync(kFullMask, s1, 16));
 }
-__device__ __forceinline__ void sym_col_flush(uint64_t (&k0)[4], const uint64_t (&k1)[4], float* colacc, int lane) {
+__device__ __forceinline__ void sym_col_flush(uint64_t (&k0)[4], const uint64_t (&k1)[4], float* colacc, int lane,
+                                              bool skip_red = false) {
   const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {                 // xor 8: keep r = 2 b4 + b3
@@ -465,6 +466,10 @@ __device__ __forceinline__ void sym_col_flush(uint64_t (&k0)[4], const uint64_t 
     float c0, c1;
     unpack_f32x2(k0[ch], c0, c1);
     out[ch] = (b2 ? c1 : c0) + __shfl_xor_sync(kFullMask, b2 ? c0 : c1, 4);
+  }
+  if (skip_red) {                                  // timing experiment (debug flag 256): results are wrong
+    if (out[0] + out[1] + out[2] + out[3] == -1.f) colacc[0] = 0.f;
+    return;
   }
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) atomicAdd(colacc + ch * 32 * 4, out[ch]);
@@ -579,14 +584,20 @@ __device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, 
 // =================================================================================================
 // forward, pass A: row statistics over all column tiles
 // =================================================================================================
-template <int BN, bool SYM>
-__global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constant__ CUtensorMap tmap_a,
+// NWG = epilogue warpgroups (2: 384 threads / 168 registers; 3: 512 threads / 128 registers, BN = 128 only, an
+// experiment behind SPCL_WG3=1).
+template <int BN, bool SYM, int NWG>
+__global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                             const __grid_constant__ CUtensorMap tmap_b, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const SmemView sm = carve(smem_raw, p, BN, false);
   Barriers* bar = sm.bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kSub = BN / TILE;                    // 128-column blocks per tile
+  static_assert(NWG == 2 || (NWG == 3 && BN == TILE), "three epilogue warpgroups take whole 128-column tiles in turn");
+  // roles (shadow the file-level constants of the 384-thread kernels)
+  constexpr int kEpilogueWarps = 4 * NWG, kProducerWarp = kEpilogueWarps, kMmaWarp0 = kEpilogueWarps + 1,
+                kAllocWarp = kEpilogueWarps + 2, kMmaWarp1 = kEpilogueWarps + 3;
   constexpr int kBufs = static_cast<int>(kTmemCols) / BN;
 
   if (warp == kMmaWarp0 && lane == 0)
@@ -714,7 +725,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
         rsig = p.sig[rb0 + c.I];
         mask_grp = 0xffffffffu;
       }
-      const bool mine = (kSub == 2) || (static_cast<int>(c.it & 1) == wg);
+      const bool mine = (kSub == 2) || (static_cast<int>(c.it % NWG) == wg);
       if (mine) {
         const int buf = rb.idx;
         const uint32_t bph = rb.ph;
@@ -722,11 +733,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
           mask_grp = c.t >> 5;
           mask = slow_mask(mask_grp);
         }
-        const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
+        const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u && !(p.dbg & 1024);   // 1024: timing experiment
         const uint32_t jb = block_of(c.t);
         const int64_t j0 = static_cast<int64_t>(jb) * TILE;
         const bool inside = jb < ct128 && !(SYM && jb < row_jb);
-        const bool cols = SYM && jb > row_jb;
+        const bool cols = SYM && (jb > row_jb || (p.dbg & 1024));
         mbar_wait_warp(&bar->s_full[buf], bph, lane);
         TRACE(2 + warp, c.it, 0);
         tc_fence_after();
@@ -750,7 +761,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) stats_kernel(const __grid_constan
               if (ch < 3) tmem_wait_ld();
               sym_col_step1(col, k0[ch], k1[ch], lane);
             }
-            if (!(p.dbg & 1)) sym_col_flush(k0, k1, reinterpret_cast<float*>(p.acc + j0 + sym_col), lane);
+            if (!(p.dbg & (1 | 512))) sym_col_flush(k0, k1, reinterpret_cast<float*>(p.acc + j0 + sym_col), lane, (p.dbg & 256) != 0);
           } else {
             const int64_t dj = gi - j0;
             const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
@@ -1657,6 +1668,15 @@ static bool sym_enabled() {
   return env != 0 && !(g_dbg & 64);
 }
 
+static bool wg3_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("SPCL_WG3");
+    env = (e == nullptr) ? 0 : (e[0] != '0');
+  }
+  return env != 0 || (g_dbg & 128);
+}
+
 // minimax polynomials of 2^f on [-0.5, 0.5] (relative error 2.7e-6 / 7.5e-5)
 static const double kPoly4[5] = {0.999999261492568, 0.6931218184520522, 0.24024745066719647, 0.05591783074149139,
                                  0.00957007737459198};
@@ -1747,7 +1767,11 @@ using namespace spcl;
 static int launch_stats(const tc::Params& p, const void* zb, int64_t n_pad, int32_t d_pad, bool sym, int part,
                         int nparts, const CUtensorMap& tmap128, cudaStream_t s) {
   // 128 x 256 tiles while a 256-row slot ring of >= 2 slots fits (d <= 128), else 128 x 128
-  const bool wide = tc::pick_slots(p.dc, 256, false) >= 2 && !(tc::g_dbg & 16);
+  // SPCL_WG3=1 / debug flag 128: three epilogue warpgroups on 128 x 128 tiles instead of two on 128 x 256.  Measured
+  // equal at cfg3 (264 us both): the third warp per scheduler is paid for by 128-register spills of the per-tile
+  // loop state (~2000 cycles between two tiles of a warpgroup); kept as an experiment, off by default.
+  const bool wg3 = sym && tc::wg3_enabled();
+  const bool wide = !wg3 && tc::pick_slots(p.dc, 256, false) >= 2 && !(tc::g_dbg & 16);
   const int bn = wide ? 256 : 128;
   tc::Params pa = p;
   pa.CT = ceil_div(n_pad, static_cast<int64_t>(bn));
@@ -1768,14 +1792,15 @@ static int launch_stats(const tc::Params& p, const void* zb, int64_t n_pad, int3
     pa.vgrid = grid * static_cast<unsigned>(nparts);
     pa.vblock0 = grid * static_cast<unsigned>(part);
   }
-  auto launch = [&](auto kernel) -> int {
+  auto launch = [&](auto kernel, int nthreads) -> int {
     const int r2 = tc::set_smem(kernel, smem);
     if (r2 != SPCL_OK) return r2;
-    kernel<<<grid, tc::NTHREADS, smem, s>>>(tmap128, tmapb, pa);
+    kernel<<<grid, nthreads, smem, s>>>(tmap128, tmapb, pa);
     return SPCL_OK;
   };
-  if (wide) rc = sym ? launch(tc::stats_kernel<256, true>) : launch(tc::stats_kernel<256, false>);
-  else rc = sym ? launch(tc::stats_kernel<128, true>) : launch(tc::stats_kernel<128, false>);
+  if (wg3) rc = launch(tc::stats_kernel<128, true, 3>, 512);
+  else if (wide) rc = sym ? launch(tc::stats_kernel<256, true, 2>, 384) : launch(tc::stats_kernel<256, false, 2>, 384);
+  else rc = sym ? launch(tc::stats_kernel<128, true, 2>, 384) : launch(tc::stats_kernel<128, false, 2>, 384);
   if (rc != SPCL_OK) return rc;
   SPCL_LAUNCH_CHECK("spcl_supcon_fwd_bf16/stats");
   return SPCL_OK;

@@ -36,6 +36,13 @@ __global__ void k(float* out, unsigned long long* cyc, float seed) {
       if (KIND == 6) a[i] = fmaf(a[i], b[i], b[(i + 1) % CH]);                              // FFMA (3 regs)
       if (KIND == 7) { a[i] = fmaf(a[i], b[i], b[(i + 1) % CH]); asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(c2), "l"(c3)); }  // FFMA + FFMA2
       if (KIND == 8) asm volatile("shf.l.wrap.b32 %0, %0, %0, 23;" : "+r"(u[i]));           // SHF (ALU)
+      if (KIND == 10) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(c2), "l"(c3));
+                        asm volatile("shf.l.wrap.b32 %0, %0, %0, 23;" : "+r"(u[i])); }         // FFMA2 + SHF (FMA + ALU pipes)
+      if (KIND == 11) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(c2), "l"(c3));
+                        asm volatile("shf.l.wrap.b32 %0, %0, %0, 23;" : "+r"(u[i]));
+                        if ((i & 3) == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); }   // + MUFU every 4th
+      if (KIND == 12) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(c3));
+                        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(u[(i + 1) % CH]), "r"(u[(i + 2) % CH])); }  // FADD2 + LOP3
       if (KIND == 9) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(c2), "l"(c3)); u[i] = u[i] * 0x800000u + u[(i + 1) % CH]; }  // FFMA2 + IMAD
     }
   }
@@ -87,5 +94,8 @@ int main() {
   run<5>("FFMA2+MUFU", 2);
   run<7>("FFMA+FFMA2", 2);
   run<9>("FFMA2+IMAD", 2);
+  run<10>("FFMA2+SHF", 2);
+  run<11>("FFMA2+SHF+MUFU/4", 2);
+  run<12>("FADD2+LOP3", 2);
   return 0;
 }
