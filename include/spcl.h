@@ -137,6 +137,18 @@ int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz,
                         const float* scalars, const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
                         int mode, float* dz, int64_t lddz, spcl_stream_t stream);
 
+/* Label form (labels != NULL, mode NONE / HARD / SOFT) of the two calls above on a (row block, column range)
+ * grid: the reference's own batch sizes (N = 60 .. 512, semi_seg/hooks/infonce.py:171-195) give the row-only
+ * grid of spcl_supcon_fwd_f32 at most 8 CTAs.  acc: float [n_total][4] scratch (16-byte aligned), zeroed by the
+ * call; dz is zeroed by the call when more than one CTA adds to a row.  Same results up to summation order. */
+int spcl_supcon_fwd_f32_split(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                              int64_t row_begin, int64_t row_end, float inv_tau, float gamma, int mode, float* acc,
+                              float* row_stats, int64_t stats_stride, float* partials, spcl_stream_t stream);
+int spcl_supcon_bwd_f32_split(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
+                              const float* row_stats, int64_t stats_stride, const float* scalars,
+                              const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
+                              int mode, float* dz, int64_t lddz, spcl_stream_t stream);
+
 /* ---- scalar epilogue (after the optional all-reduce of partials) ------------------------------
  * scalars = { loss, ratio, scale, scale / N }; scale = 1/ratio if correct_grad and ratio > 0
  * (contrast_loss3.py:189-201).  A NaN loss is reported by the host wrapper as RuntimeError (:203). */

@@ -41,6 +41,10 @@ SIGNATURES = {
                             _i64, _ptr, _ptr],
     "spcl_supcon_bwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _f32,
                             _f32, _c.c_int, _ptr, _i64, _ptr],
+    "spcl_supcon_fwd_f32_split": [_ptr, _i64, _i32, _i64, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr, _i64,
+                                  _ptr, _ptr],
+    "spcl_supcon_bwd_f32_split": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _f32, _f32,
+                                  _c.c_int, _ptr, _i64, _ptr],
     "spcl_supcon_finalize": [_ptr, _i64, _c.c_int, _ptr, _ptr],
 }
 OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error")

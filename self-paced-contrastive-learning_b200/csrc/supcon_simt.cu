@@ -334,6 +334,223 @@ __global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float* __restrict
   }
 }
 
+// =================================================================================================
+// Split kernels for the label form (modes NONE / HARD / SOFT): the (row block, column range) grid instead of one
+// CTA per 64 rows.  The reference's own batch sizes (N = 60 .. 512) give the row-only grid 1 .. 8
+// CTAs on 148 SMs, each walking every column twice: 500 us per N = 512 problem, all latency.  Here a CTA owns one
+// 64 x 64 tile (a few when N is large), partial row sums meet in `acc` through atomics exactly like the
+// tensor-core path (acc: float4 per anchor = rowsum, c, sum P <z_i,z_j> | sum P W LLH, sum P W), and the per-row
+// epilogue is its own small kernel.  Same arithmetic per pair as fwd_kernel / bwd_kernel above.
+// =================================================================================================
+struct Split {
+  int ct_per_cta;      // consecutive 64-column tiles one CTA walks
+};
+
+__device__ __forceinline__ void split_rows(const Args& p, int64_t i0, int ty, int64_t (&gi)[4], int (&li)[4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    gi[a] = i0 + ty * 4 + a;
+    li[a] = gi[a] < p.N ? p.labels[gi[a]] : 0;
+  }
+}
+
+// PASS 0: rowsum, c, sum P <z_i, z_j>;  PASS 1: sum P W LLH, sum P W (needs the complete rowsum of PASS 0)
+template <int PASS>
+__global__ void __launch_bounds__(NT) fwd_split_kernel(Args p, Split sp, float4* __restrict__ acc) {
+  __shared__ Smem sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+  int64_t gi[4];
+  int li[4];
+  split_rows(p, i0, ty, gi, li);
+  float logD[4] = {0.f, 0.f, 0.f, 0.f};
+  if (PASS == 1) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (gi[a] < p.N) logD[a] = shift + logf(acc[gi[a]].x);
+  }
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float d[4][4];
+  const int64_t jt0 = static_cast<int64_t>(blockIdx.y) * sp.ct_per_cta;
+  for (int t = 0; t < sp.ct_per_cta; ++t) {
+    const int64_t j0 = (jt0 + t) * BN;
+    if (j0 >= p.N) break;
+    tile_dot(p, sm, i0, j0, d);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t gj = j0 + tx + 16 * b;
+      if (gj >= p.N) continue;
+      const int lj = p.labels[gj];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (gi[a] == gj || gi[a] >= p.N) continue;
+        const bool pos = li[a] == lj;
+        const float s = d[a][b] * p.inv_tau;
+        if (PASS == 0) {
+          s0[a] += expf(s - shift);
+          if (pos) {
+            s1[a] += 1.f;
+            s2[a] += d[a][b];
+          }
+        } else if (pos) {
+          const float llh = s - logD[a];
+          const float w = sp_weight(-llh, p.gamma, p.inv_gamma, p.mode);
+          s0[a] = fmaf(w, llh, s0[a]);
+          s1[a] += w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float r0 = row_sum16(s0[a]), r1 = row_sum16(s1[a]), r2 = row_sum16(s2[a]);
+    if (tx != 0 || gi[a] >= p.row_end) continue;
+    float* out = reinterpret_cast<float*>(acc + gi[a]);
+    if (PASS == 0) {
+      if (r0 != 0.f) atomicAdd(out + 0, r0);
+      if (r1 != 0.f) atomicAdd(out + 1, r1);
+      if (p.mode == SPCL_MODE_NONE && r2 != 0.f) atomicAdd(out + 2, r2);
+    } else if (r1 != 0.f) {
+      atomicAdd(out + 2, r0);
+      atomicAdd(out + 3, r1);
+    }
+  }
+}
+
+// row_stats planes {logD, 1/c, A, u} and the three partial sums from the complete acc (cf. fwd_kernel's epilogue)
+__global__ void __launch_bounds__(256) row_finalize_split_kernel(const float4* __restrict__ acc, int64_t row_begin,
+                                                                 int64_t row_end, int64_t sld, float inv_tau,
+                                                                 int mode, float* __restrict__ row_stats,
+                                                                 float* __restrict__ partials) {
+  __shared__ float red[3][8];
+  const int64_t gi = row_begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float l = 0.f, w = 0.f, c = 0.f;
+  if (gi < row_end) {
+    const float4 a = acc[gi];
+    const float logD = inv_tau + logf(a.x);
+    const float cnt = a.y;
+    const float wl = mode == SPCL_MODE_NONE ? a.z * inv_tau - cnt * logD : a.z;
+    const float wp = mode == SPCL_MODE_NONE ? cnt : a.w;
+    const float invc = 1.f / cnt;                    // c == 0 -> inf -> NaN loss, like the reference's 0/0
+    const float A = wp * invc;
+    row_stats[gi] = logD;
+    row_stats[sld + gi] = invc;
+    row_stats[2 * sld + gi] = A;
+    row_stats[3 * sld + gi] = A / a.x;
+    l = wl * invc;
+    w = wp;
+    c = cnt;
+  }
+  l = warp_sum(l);
+  w = warp_sum(w);
+  c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = l; red[1][warp] = w; red[2][warp] = c; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
+    atomicAdd(&partials[threadIdx.x], s);
+  }
+}
+
+template <int DV>
+__global__ void __launch_bounds__(NT) bwd_split_kernel(Args p, Split sp, const float* __restrict__ row_stats,
+                                                       int64_t sld, const float* __restrict__ scalars,
+                                                       const float* __restrict__ grad_out, float* __restrict__ dz,
+                                                       int64_t lddz) {
+  __shared__ Smem sm;
+  __shared__ float ts[BM][BN + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+  int64_t gi[4];
+  int li[4];
+  split_rows(p, i0, ty, gi, li);
+  float4 si[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    si[a] = gi[a] < p.N ? make_float4(row_stats[gi[a]], row_stats[sld + gi[a]], 0.f, row_stats[3 * sld + gi[a]])
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  float dzacc[4][DV];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < DV; ++c) dzacc[a][c] = 0.f;
+
+  float d[4][4];
+  const int64_t jt0 = static_cast<int64_t>(blockIdx.y) * sp.ct_per_cta;
+  for (int t = 0; t < sp.ct_per_cta; ++t) {
+    const int64_t j0 = (jt0 + t) * BN;
+    if (j0 >= p.N) break;
+    tile_dot(p, sm, i0, j0, d);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int cj = tx + 16 * b;
+      const int64_t gj = j0 + cj;
+      const bool col_ok = gj < p.N;
+      const int lj = col_ok ? p.labels[gj] : 0;
+      const float4 sj = col_ok ? make_float4(row_stats[gj], row_stats[sld + gj], 0.f, row_stats[3 * sld + gj])
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float tv = 0.f;
+        if (col_ok && gi[a] < p.N && gi[a] != gj) {
+          const float s = d[a][b] * p.inv_tau;
+          tv = expf(s - shift) * (si[a].w + sj.w);
+          if (li[a] == lj)
+            tv -= sp_weight(si[a].x - s, p.gamma, p.inv_gamma, p.mode) * si[a].y +
+                  sp_weight(sj.x - s, p.gamma, p.inv_gamma, p.mode) * sj.y;
+        }
+        ts[ty * 4 + a][cj] = tv;
+      }
+    }
+    __syncthreads();
+    const int jmax = static_cast<int>(min(static_cast<int64_t>(BN), p.N - j0));
+    for (int jj = 0; jj < jmax; ++jj) {
+      const float* zrow = p.z + (j0 + jj) * p.ldz;
+      float tv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) tv[a] = ts[ty * 4 + a][jj];
+#pragma unroll
+      for (int c = 0; c < DV; ++c) {
+        const int col = tx + 16 * c;
+        const float zv = col < p.d ? zrow[col] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dzacc[a][c] = fmaf(tv[a], zv, dzacc[a][c]);
+      }
+    }
+    __syncthreads();
+  }
+
+  const float coef = grad_out[0] * scalars[3] * p.inv_tau;
+  const bool single = gridDim.y == 1;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (gi[a] >= p.row_end) continue;
+    float* out = dz + (gi[a] - p.row_begin) * lddz;
+#pragma unroll
+    for (int c = 0; c < DV; ++c) {
+      const int col = tx + 16 * c;
+      if (col >= p.d) continue;
+      if (single) out[col] = dzacc[a][c] * coef;
+      else atomicAdd(out + col, dzacc[a][c] * coef);
+    }
+  }
+}
+
+// column tiles per CTA so that the grid has about two CTAs per SM
+static Split pick_split(int64_t rows, int64_t n_total, unsigned& gy) {
+  const int64_t rb = ceil_div(rows, static_cast<int64_t>(BM)), ct = ceil_div(n_total, static_cast<int64_t>(BN));
+  int64_t per = (rb * ct) / 296;
+  if (per < 1) per = 1;
+  if (per > ct) per = ct;
+  gy = static_cast<unsigned>(ceil_div(ct, per));
+  return Split{static_cast<int>(per)};
+}
+
 __global__ void finalize_kernel(const float* __restrict__ partials, float n_total, int correct_grad,
                                 float* __restrict__ scalars) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -405,5 +622,62 @@ extern "C" int spcl_supcon_finalize(const float* partials, int64_t n_total, int 
   simt::finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, static_cast<float>(n_total),
                                                                         correct_grad, scalars);
   SPCL_LAUNCH_CHECK("spcl_supcon_finalize");
+  return SPCL_OK;
+}
+
+// ---- label form on the (row block, column range) grid: same contract as spcl_supcon_fwd_f32 / _bwd_f32 with
+// labels != NULL and mode in {NONE, HARD, SOFT}; acc: float [n_total][4] scratch, zeroed by the call.
+extern "C" int spcl_supcon_fwd_f32_split(const float* z, int64_t n_total, int32_t d, int64_t ldz,
+                                         const int32_t* labels, int64_t row_begin, int64_t row_end, float inv_tau,
+                                         float gamma, int mode, float* acc, float* row_stats, int64_t stats_stride,
+                                         float* partials, spcl_stream_t stream) {
+  int rc = simt::check_common(z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (mode == SPCL_MODE_EXCL) return SPCL_ERR_UNSUPPORTED;
+  if (acc == nullptr || row_stats == nullptr || partials == nullptr || stats_stride < n_total ||
+      (reinterpret_cast<uintptr_t>(acc) & 15))
+    return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t rows = row_end - row_begin;
+  unsigned gy = 1;
+  const simt::Split sp = simt::pick_split(rows, n_total, gy);
+  const dim3 grid(static_cast<unsigned>(ceil_div(rows, static_cast<int64_t>(simt::BM))), gy);
+  float4* acc4 = reinterpret_cast<float4*>(acc);
+  SPCL_CUDA_TRY(cudaMemsetAsync(acc + row_begin * 4, 0, static_cast<size_t>(rows) * 16, s));
+  simt::fwd_split_kernel<0><<<grid, simt::NT, 0, s>>>(a, sp, acc4);
+  SPCL_LAUNCH_CHECK("spcl_supcon_fwd_f32_split/stats");
+  if (mode != SPCL_MODE_NONE) {
+    simt::fwd_split_kernel<1><<<grid, simt::NT, 0, s>>>(a, sp, acc4);
+    SPCL_LAUNCH_CHECK("spcl_supcon_fwd_f32_split/sp");
+  }
+  simt::row_finalize_split_kernel<<<static_cast<unsigned>(ceil_div(rows, static_cast<int64_t>(256))), 256, 0, s>>>(
+      acc4, row_begin, row_end, stats_stride, inv_tau, mode, row_stats, partials);
+  SPCL_LAUNCH_CHECK("spcl_supcon_fwd_f32_split/row_finalize");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_bwd_f32_split(const float* z, int64_t n_total, int32_t d, int64_t ldz,
+                                         const int32_t* labels, const float* row_stats, int64_t stats_stride,
+                                         const float* scalars, const float* grad_out, int64_t row_begin,
+                                         int64_t row_end, float inv_tau, float gamma, int mode, float* dz,
+                                         int64_t lddz, spcl_stream_t stream) {
+  int rc = simt::check_common(z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, mode);
+  if (rc != SPCL_OK) return rc;
+  if (mode == SPCL_MODE_EXCL) return SPCL_ERR_UNSUPPORTED;
+  if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d ||
+      stats_stride < n_total)
+    return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t rows = row_end - row_begin;
+  unsigned gy = 1;
+  const simt::Split sp = simt::pick_split(rows, n_total, gy);
+  const dim3 grid(static_cast<unsigned>(ceil_div(rows, static_cast<int64_t>(simt::BM))), gy);
+  if (gy > 1) SPCL_CUDA_TRY(cudaMemsetAsync(dz, 0, static_cast<size_t>(rows) * lddz * sizeof(float), s));
+  if (d <= 64) simt::bwd_split_kernel<4><<<grid, simt::NT, 0, s>>>(a, sp, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else if (d <= 128) simt::bwd_split_kernel<8><<<grid, simt::NT, 0, s>>>(a, sp, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else simt::bwd_split_kernel<16><<<grid, simt::NT, 0, s>>>(a, sp, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  SPCL_LAUNCH_CHECK("spcl_supcon_bwd_f32_split");
   return SPCL_OK;
 }

@@ -19,6 +19,8 @@ Extra keyword arguments (accepted through the reference's ``**kwargs``):
                 (:203-204), which costs one host sync per call; False leaves the check to the caller.
 ``validate``    True (default) keeps the reference's ``assert is_normalized`` (:154), active only
                 when Python runs without ``-O``, exactly like the reference.
+``cuda_graph``  False (default).  True: forward + backward of a call run as ONE CUDA-graph replay (captured once
+                per batch shape / gamma; labels form only) -- the reference's batch sizes are launch-bound.
 """
 from __future__ import annotations
 
@@ -111,8 +113,11 @@ class _Diagnostics:
 
 def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Optional[Tensor] = None,
                 temperature: float = 0.07, gamma: float = 1e6, mode: int = nat.MODE_NONE,
-                correct_grad: bool = False, precision: str = "auto"):
-    """Functional form.  -> (loss 0-d, scalars[4] = loss/ratio/scale/scale_over_N, aux dict)."""
+                correct_grad: bool = False, precision: str = "auto", graph_cache: Optional[dict] = None):
+    """Functional form.  -> (loss 0-d, scalars[4] = loss/ratio/scale/scale_over_N, aux dict).
+
+    ``graph_cache``: a dict owned by the caller; when given (labels form only), forward + backward of this call
+    run as one CUDA-graph replay (``ops.GraphRunner``), captured once per (n, d, hyper-parameters)."""
     if proj_feat1.shape != proj_feat2.shape:
         raise AssertionError((proj_feat1.shape, proj_feat2.shape))
     if not (proj_feat1.is_cuda and proj_feat2.is_cuda):
@@ -130,8 +135,18 @@ def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Op
     else:                                     # :140-143  SimCLR
         labels = torch.arange(n, dtype=torch.int32, device=dev)
     use_tc = _pick_tc(precision, 2 * n, tri is not None, int(mode))
-    scalars, row_stats, _, _, _ = ops.supcon_fwd(z1, z2, labels, tri, float(temperature), float(gamma), int(mode),
-                                                 bool(correct_grad), use_tc)
+    if graph_cache is not None and tri is None and int(mode) != nat.MODE_EXCL and not torch.compiler.is_compiling():
+        key = (n, z1.shape[1], str(dev), float(temperature), float(gamma), int(mode), bool(correct_grad), use_tc)
+        runner = graph_cache.get(key)
+        if runner is None:
+            if len(graph_cache) >= 8:             # gamma changes once per epoch: keep the cache small
+                graph_cache.pop(next(iter(graph_cache)))
+            runner = graph_cache[key] = ops.GraphRunner(n, z1.shape[1], dev, temperature, gamma, mode, correct_grad,
+                                                        use_tc)
+        scalars, row_stats = ops.supcon_fwd_graphed(z1, z2, labels, runner)
+    else:
+        scalars, row_stats = ops.supcon_fwd_eager(z1, z2, labels, tri, float(temperature), float(gamma), int(mode),
+                                                  bool(correct_grad), use_tc)
     return scalars[0], scalars, dict(labels=labels, tri=tri, row_stats=row_stats, use_tc=use_tc)
 
 
@@ -143,6 +158,7 @@ class _FusedSupConBase(nn.Module):
         self._precision = kwargs.pop("precision", "auto")
         self._check_nan = bool(kwargs.pop("check_nan", True))
         self._validate = bool(kwargs.pop("validate", True))
+        self._graphs = {} if bool(kwargs.pop("cuda_graph", False)) else None
         self._diag = None
         self._scalars = None
         self._ratio_cache = None
@@ -158,7 +174,8 @@ class _FusedSupConBase(nn.Module):
         assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
         gamma, mode, cg = self._gamma_mode_cg()
         loss, scalars, aux = supcon_loss(proj_feat1, proj_feat2, target=target, mask=mask, temperature=self._t,
-                                         gamma=gamma, mode=mode, correct_grad=cg, precision=self._precision)
+                                         gamma=gamma, mode=mode, correct_grad=cg, precision=self._precision,
+                                         graph_cache=self._graphs)
         self._scalars = scalars.detach()
         self._ratio_cache = None
         self._diag = _Diagnostics(proj_feat1, proj_feat2, aux["labels"], aux["tri"], aux["row_stats"], self._t,

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -87,6 +88,13 @@ def tri_codes(mask: Tensor, n: int, device) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 # fused loss
 # --------------------------------------------------------------------------------------------------
+def _f32_split(has_labels: bool, mode: int) -> bool:
+    """fp32 path: label form with W in {1, hard, soft} runs on the 2-D grid kernels; the tri-state ``mask=`` form and
+    ``exclude_other_pos`` keep the row-grid kernels.  SPCL_F32_SPLIT=0 forces the row grid (A/B switch)."""
+    return has_labels and mode != nat.MODE_EXCL and os.environ.get("SPCL_F32_SPLIT", "1") != "0"
+
+
+
 @torch.library.custom_op("spcl::supcon_fwd", mutates_args=(), device_types="cuda")
 def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[Tensor], temperature: float,
                gamma: float, mode: int, correct_grad: bool, use_tc: bool
@@ -141,9 +149,15 @@ def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[T
             labels_full = torch.empty(0, dtype=torch.int32, device=dev)
         zpack = torch.cat([z1, z2], dim=0)
         sig = torch.empty(0, 4, dtype=torch.int32, device=dev)
-        nat.call("spcl_supcon_fwd_f32", _ptr(zpack), N, d, zpack.stride(0),
-                 _ptr(labels_full) if labels is not None else None, _ptr(tri), n, 0, N, inv_tau, float(gamma),
-                 int(mode), _ptr(row_stats), n_pad, _ptr(partials), st)
+        if _f32_split(labels is not None, mode):
+            # (row block, column range) grid: the batch sizes the reference trains with fill the machine
+            acc = torch.empty(N, 4, dtype=torch.float32, device=dev)
+            nat.call("spcl_supcon_fwd_f32_split", _ptr(zpack), N, d, zpack.stride(0), _ptr(labels_full), 0, N,
+                     inv_tau, float(gamma), int(mode), _ptr(acc), _ptr(row_stats), n_pad, _ptr(partials), st)
+        else:
+            nat.call("spcl_supcon_fwd_f32", _ptr(zpack), N, d, zpack.stride(0),
+                     _ptr(labels_full) if labels is not None else None, _ptr(tri), n, 0, N, inv_tau, float(gamma),
+                     int(mode), _ptr(row_stats), n_pad, _ptr(partials), st)
     nat.call("spcl_supcon_finalize", _ptr(partials), N, int(bool(correct_grad)), _ptr(scalars), st)
     return scalars, row_stats, zpack, labels_full, sig
 
@@ -181,6 +195,10 @@ def supcon_bwd(grad_loss: Tensor, zpack: Tensor, labels_full: Tensor, sig: Tenso
         nat.call("spcl_supcon_bwd_bf16", _ptr(zpack), N, n_pad, d_pad, d, _ptr(labels_full), _ptr(sig),
                  _ptr(row_stats), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz),
                  dz.stride(0), st)
+    elif _f32_split(tri is None, mode):
+        nat.call("spcl_supcon_bwd_f32_split", _ptr(zpack), N, d, zpack.stride(0), _ptr(labels_full), _ptr(row_stats),
+                 row_stats.stride(0), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz),
+                 dz.stride(0), st)
     else:
         nat.call("spcl_supcon_bwd_f32", _ptr(zpack), N, d, zpack.stride(0),
                  _ptr(labels_full) if tri is None else None, _ptr(tri), n, _ptr(row_stats),
@@ -213,6 +231,110 @@ def _supcon_backward(ctx, g_scalars, g_stats, g_zpack, g_labels, g_sig):
 
 
 supcon_fwd.register_autograd(_supcon_backward, setup_context=_supcon_setup)
+
+
+class _DirectSupCon(torch.autograd.Function):
+    """The same two entry points without the ``torch.library`` dispatch, for eager callers.
+
+    A Python custom op costs ~100 us of dispatcher / fake-tensor bookkeeping per call on the host -- more than the
+    kernels of one N = 512 problem.  ``spcl::supcon_fwd`` / ``spcl::supcon_bwd`` stay the registered op surface
+    (``torch.compile``, ``opcheck``, export); the ``nn.Module``s call this when they run eagerly."""
+
+    @staticmethod
+    def forward(ctx, z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc):
+        scalars, row_stats, zpack, labels_full, sig = supcon_fwd._init_fn(z1, z2, labels, tri, temperature, gamma,
+                                                                          mode, correct_grad, use_tc)
+        ctx.save_for_backward(zpack, labels_full, sig, tri, row_stats, scalars)
+        ctx.hp = (temperature, gamma, mode, use_tc, z1.shape[0], z1.shape[1])
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(row_stats)
+        return scalars, row_stats
+
+    @staticmethod
+    def backward(ctx, g_scalars, _g_stats):
+        if g_scalars is None:
+            return (None,) * 9
+        zpack, labels_full, sig, tri, row_stats, scalars = ctx.saved_tensors
+        temperature, gamma, mode, use_tc, n, d = ctx.hp
+        dz = supcon_bwd._init_fn(g_scalars[0], zpack, labels_full, sig, tri, row_stats, scalars, temperature, gamma,
+                                 mode, use_tc, n, d)
+        return dz[:n], dz[n:], None, None, None, None, None, None, None
+
+
+def supcon_fwd_eager(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc):
+    """-> (scalars[4], row_stats): ``spcl::supcon_fwd`` under tracing / compilation, the direct route otherwise."""
+    if torch.compiler.is_compiling():
+        scalars, row_stats, _, _, _ = supcon_fwd(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
+        return scalars, row_stats
+    return _DirectSupCon.apply(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
+
+
+class GraphRunner:
+    """fwd + bwd of one loss call as ONE CUDA-graph replay, for fixed (n, d) and hyper-parameters.
+
+    The reference's batch sizes (N = 60 .. 512) are launch-bound: 5 kernels + 2 memsets per call.  The graph holds
+    the forward and, with an upstream gradient of 1, the backward (the loss is a scalar, so d loss / d z only scales);
+    inputs are copied into static buffers.  Labels form only (no tri-state mask)."""
+
+    def __init__(self, n: int, d: int, device, temperature: float, gamma: float, mode: int, correct_grad: bool,
+                 use_tc: bool):
+        self.key = (n, d, str(device), float(temperature), float(gamma), int(mode), bool(correct_grad), bool(use_tc))
+        self.n, self.d = n, d
+        g = torch.Generator(device="cpu").manual_seed(0)
+        warm = torch.nn.functional.normalize(torch.randn(2, n, d, generator=g), dim=2).to(device)
+        self.z1, self.z2 = warm[0].contiguous(), warm[1].contiguous()
+        self.labels = torch.arange(n, dtype=torch.int32, device=device)
+        self.g = torch.ones(1, dtype=torch.float32, device=device)
+        hp = (float(temperature), float(gamma), int(mode))
+
+        def body():
+            scalars, row_stats, zpack, labels_full, sig = supcon_fwd._init_fn(
+                self.z1, self.z2, self.labels, None, hp[0], hp[1], hp[2], bool(correct_grad), bool(use_tc))
+            dz = supcon_bwd._init_fn(self.g, zpack, labels_full, sig, None, row_stats, scalars, hp[0], hp[1], hp[2],
+                                     bool(use_tc), n, d)
+            return scalars, row_stats, dz
+
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+
+    def run(self, z1: Tensor, z2: Tensor, labels: Tensor):
+        """-> static (scalars[4], row_stats[4, n_pad], dz[2n, d] for an upstream gradient of 1); overwritten by the
+        next run."""
+        self.z1.copy_(z1)
+        self.z2.copy_(z2)
+        self.labels.copy_(labels)
+        self.graph.replay()
+        return self.out
+
+
+class _GraphedSupCon(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, labels, runner):
+        scalars, row_stats, dz = runner.run(z1.detach(), z2.detach(), labels)
+        ctx.dz = dz.clone()                       # the runner's buffers belong to its next replay
+        ctx.n = z1.shape[0]
+        ctx.set_materialize_grads(False)
+        row_stats = row_stats.clone()
+        ctx.mark_non_differentiable(row_stats)
+        return scalars.clone(), row_stats
+
+    @staticmethod
+    def backward(ctx, g_scalars, _g_stats):
+        if g_scalars is None:
+            return None, None, None, None
+        dz = ctx.dz * g_scalars[0]
+        return dz[:ctx.n], dz[ctx.n:], None, None
+
+
+def supcon_fwd_graphed(z1, z2, labels, runner: GraphRunner):
+    return _GraphedSupCon.apply(z1, z2, labels, runner)
 
 
 # --------------------------------------------------------------------------------------------------

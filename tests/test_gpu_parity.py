@@ -449,3 +449,48 @@ def test_stats_parts_plus_finish_equals_fused_forward(n, d, kind, mode, nparts):
         np.testing.assert_allclose(other_rs[2], rs_one[2], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(other_rs[3], rs_one[3], rtol=1e-4)
         np.testing.assert_allclose(other_pt, pt_one, rtol=2e-5)
+
+
+# ---- eager direct route / CUDA-graph replay == registered custom ops ----------------------------
+@pytest.mark.parametrize("n,d,mode,precision", [(64, 128, "soft", "fp32"), (256, 256, "hard", "fp32"),
+                                                 (300, 128, "soft", "bf16")])
+def test_cuda_graph_replay_matches_eager(n, d, mode, precision):
+    labels = acdc_meta_labels(n)["patient"]
+    outs = {}
+    for graphed in (False, True):
+        crit = spcl_b200.SelfPacedSupConLoss(weight_update=mode, correct_grad=True, precision=precision,
+                                             cuda_graph=graphed)
+        crit.set_gamma(5.0)
+        res = []
+        for seed in (0, 1, 2):                      # three different batches through the same module / graph
+            z1, z2 = make_views(labels, d, sigma=0.7, seed=seed)
+            a, b = z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True)
+            loss = crit(a, b, target=labels.tolist())
+            (3.0 * loss).backward()
+            res.append((loss.item(), crit.downgrade_ratio, a.grad.clone(), b.grad.clone()))
+        outs[graphed] = res
+    for (l0, r0, ga0, gb0), (l1, r1, ga1, gb1) in zip(outs[False], outs[True]):
+        # same kernels, same inputs: only the atomics' summation order differs
+        assert np.isclose(l0, l1, rtol=1e-5) and np.isclose(r0, r1, rtol=1e-5)
+        tol = 2e-5 * max(ga0.abs().max().item(), 1e-12) if precision == "fp32" else 2e-3 * ga0.abs().max().item()
+        assert (ga0 - ga1).abs().max().item() <= tol and (gb0 - gb1).abs().max().item() <= tol
+
+
+def test_direct_route_matches_custom_op():
+    """The modules' eager route and the registered ``spcl::supcon_fwd`` op give the same loss and gradients."""
+    from spcl_b200 import ops
+    n, d = 192, 128
+    labels = acdc_meta_labels(n)["cycle"].int().cuda()
+    z1, z2 = make_views(labels.cpu(), d, sigma=0.7, seed=5)
+    outs = []
+    for direct in (False, True):
+        a, b = z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True)
+        if direct:
+            scalars, _ = ops.supcon_fwd_eager(a, b, labels, None, 0.07, 4.0, nat.MODE_SOFT, True, False)
+        else:
+            scalars = ops.supcon_fwd(a, b, labels, None, 0.07, 4.0, nat.MODE_SOFT, True, False)[0]
+        scalars[0].backward()
+        outs.append((scalars[0].item(), a.grad, b.grad))
+    assert np.isclose(outs[0][0], outs[1][0], rtol=1e-6)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-7)
