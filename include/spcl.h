@@ -89,6 +89,20 @@ int spcl_supcon_prepare_bf16(const float* z1, const float* z2, int64_t n, int64_
                              const int32_t* labels, void* zb, int64_t n_pad, int64_t d_pad, int32_t* labels_full,
                              int32_t* sig, float* partials, spcl_stream_t stream);
 
+/* ---- fused projector tail -> operands -----------------------------------------------
+ * x1, x2: float [outer][d][inner], the UN-normalised projector outputs of the two views (inner == 1: ProjectionHead's
+ * [B, C], heads.py:14-17; inner == H*W: DenseProjectionHead's NCHW, heads.py:109-115).  Same outputs as
+ * F.normalize(dim=1) (nn.py:35-36) + the [b,c,h,w] -> [b*hw, c] reshape (comparable.py:398-404) + torch.cat (:26)
+ * + spcl_supcon_prepare_bf16, in one pass: anchor h = o * inner + p of view v is row v * n + h (n = outer * inner);
+ * inv_norm: float [2n] = 1 / max(||x||, eps), kept for the backward. */
+int spcl_supcon_prepare_raw_bf16(const float* x1, const float* x2, int64_t outer, int64_t d, int64_t inner, float eps,
+                                 const int32_t* labels, void* zb, int64_t n_pad, int64_t d_pad, float* inv_norm,
+                                 int32_t* labels_full, int32_t* sig, float* partials, spcl_stream_t stream);
+/* backward of that tail from the loss gradient rows dz [2n][lddz]:
+ * gx_v[o][c][p] = inv_norm * (dz[r][c] - y[r][c] * <y[r], dz[r]>), y = x * inv_norm, r = v * n + o * inner + p */
+int spcl_supcon_raw_bwd(const float* dz, int64_t lddz, const float* x1, const float* x2, const float* inv_norm,
+                        float* gx1, float* gx2, int64_t outer, int64_t d, int64_t inner, spcl_stream_t stream);
+
 /* per-128-anchor label signatures used to skip tiles without positives: int32[n_pad/128][4] */
 int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
                          spcl_stream_t stream);

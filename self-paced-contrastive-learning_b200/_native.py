@@ -30,6 +30,9 @@ SIGNATURES = {
     "spcl_pack_views_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
     "spcl_label_block_sig": [_ptr, _i64, _i64, _ptr, _ptr],
     "spcl_supcon_prepare_bf16": [_ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr],
+    "spcl_supcon_prepare_raw_bf16": [_ptr, _ptr, _i64, _i64, _i64, _f32, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
+                                     _ptr],
+    "spcl_supcon_raw_bwd": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr],
     "spcl_supcon_fwd_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
                              _ptr, _ptr],
     "spcl_supcon_stats_part_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i32, _i32, _f32, _c.c_int, _ptr, _ptr],

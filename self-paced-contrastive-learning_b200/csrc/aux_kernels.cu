@@ -360,6 +360,164 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   if (blockIdx.x == 0 && threadIdx.x >= 128 && threadIdx.x < 131) partials[threadIdx.x - 128] = 0.f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused projector tail: un-normalised projector outputs -> normalised bf16 operands in one pass
+//   x_v: float [outer][d][inner]  (inner == 1: ProjectionHead's [B, C], heads.py:14-17; inner == H*W:
+//   DenseProjectionHead's NCHW, heads.py:109-115).  Anchor h = o * inner + p of view v is row v * n + h of zb --
+//   the [b, c, h, w] -> [b * hw, c] order of comparable.py:398-404 -- so F.normalize, the permute / reshape copy,
+//   torch.cat and the bf16 pack never touch HBM as fp32.  One CTA per 128-anchor block (labels / signature part
+//   identical to prepare_kernel).  NCHW reads are coalesced along the pixels and transposed through shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRawChunk = 64;
+
+__device__ __forceinline__ const float* raw_base(const float* x1, const float* x2, int64_t n, int64_t d, int64_t inner,
+                                                 int64_t r, bool& ok) {
+  // element (anchor r, channel c) lives at base + c * inner
+  ok = r < 2 * n;
+  if (!ok) return x1;
+  const float* x = r < n ? x1 : x2;
+  const int64_t h = r < n ? r : r - n;
+  return x + (h / inner) * d * inner + (h % inner);
+}
+
+__global__ void __launch_bounds__(256) prepare_raw_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          int64_t n, int d, int64_t inner, float eps,
+                                                          const int32_t* __restrict__ labels,
+                                                          __nv_bfloat16* __restrict__ zb, int d_pad,
+                                                          float* __restrict__ inv_norm,
+                                                          int32_t* __restrict__ labels_full, int4* __restrict__ sig,
+                                                          float* __restrict__ partials) {
+  __shared__ float tile[kRawChunk][SPCL_TILE + 1];
+  __shared__ float s_ss[2][SPCL_TILE];
+  __shared__ float s_inv[SPCL_TILE];
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * SPCL_TILE;
+  const int a = threadIdx.x & (SPCL_TILE - 1), half = threadIdx.x >> 7;
+  bool ok;
+  const float* base = raw_base(x1, x2, n, d, inner, row0 + a, ok);
+  // squared norms: thread (a, half) walks every second channel; consecutive a = consecutive pixels (coalesced)
+  float ss = 0.f;
+  if (ok)
+    for (int c = half; c < d; c += 2) {
+      const float v = base[static_cast<int64_t>(c) * inner];
+      ss = fmaf(v, v, ss);
+    }
+  s_ss[half][a] = ss;
+  __syncthreads();
+  if (threadIdx.x < SPCL_TILE) {
+    const float inv = 1.f / fmaxf(sqrtf(s_ss[0][a] + s_ss[1][a]), eps);
+    s_inv[a] = inv;
+    if (ok) inv_norm[row0 + a] = inv;
+  }
+  __syncthreads();
+  const float inv = s_inv[a];
+  for (int c0 = 0; c0 < d_pad; c0 += kRawChunk) {
+#pragma unroll 4
+    for (int cc = half; cc < kRawChunk; cc += 2) {
+      const int c = c0 + cc;
+      tile[cc][a] = (ok && c < d) ? base[static_cast<int64_t>(c) * inner] * inv : 0.f;   // L1 / L2 hit
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < SPCL_TILE * (kRawChunk / 8); g += blockDim.x) {
+      const int r = g >> 3, cg = (g & 7) << 3;
+      Vec<__nv_bfloat162, 4> o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(tile[cg + 2 * k][r], tile[cg + 2 * k + 1][r]);
+      *reinterpret_cast<Vec<__nv_bfloat162, 4>*>(zb + (row0 + r) * d_pad + c0 + cg) = o;
+    }
+    __syncthreads();
+  }
+  // labels, block signature, partial sums: as prepare_kernel
+  const int64_t n_total = 2 * n;
+  if (threadIdx.x < SPCL_TILE) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = row0 + threadIdx.x;
+    int mn = INT_MAX, mx = INT_MIN;
+    unsigned lo = 0u, hi = 0u;
+    int v = 0;
+    if (i < n_total) {
+      const int64_t h = i < n ? i : i - n;
+      v = labels != nullptr ? labels[h] : static_cast<int32_t>(h);
+      mn = mx = v;
+      const unsigned hsh = (static_cast<unsigned>(v) * 0x9E3779B1u) >> 26;
+      if (hsh < 32) lo = 1u << hsh; else hi = 1u << (hsh - 32);
+    }
+    labels_full[i] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+      hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    __shared__ int s_mn[4], s_mx[4];
+    __shared__ unsigned s_lo[4], s_hi[4];
+    if (lane == 0) {
+      s_mn[threadIdx.x >> 5] = mn;
+      s_mx[threadIdx.x >> 5] = mx;
+      s_lo[threadIdx.x >> 5] = lo;
+      s_hi[threadIdx.x >> 5] = hi;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        mn = min(mn, s_mn[k]);
+        mx = max(mx, s_mx[k]);
+        lo |= s_lo[k];
+        hi |= s_hi[k];
+      }
+      sig[blockIdx.x] = make_int4(mn, mx, static_cast<int>(lo), static_cast<int>(hi));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x >= 128 && threadIdx.x < 131) partials[threadIdx.x - 128] = 0.f;
+}
+
+// backward of the fused tail: gx[o][c][p] = inv * (dz[r][c] - y[r][c] <y[r], dz[r]>),  y = x * inv,  r = anchor row.
+// dz is row-major (coalesced along c): it goes through the shared-memory tile, x / gx stay coalesced along pixels.
+__global__ void __launch_bounds__(256) raw_bwd_kernel(const float* __restrict__ dz, int64_t lddz,
+                                                      const float* __restrict__ x1, const float* __restrict__ x2,
+                                                      const float* __restrict__ inv_norm, float* __restrict__ gx1,
+                                                      float* __restrict__ gx2, int64_t n, int d, int64_t inner) {
+  __shared__ float tile[kRawChunk][SPCL_TILE + 1];
+  __shared__ float s_dot[2][SPCL_TILE];
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * SPCL_TILE;
+  const int a = threadIdx.x & (SPCL_TILE - 1), half = threadIdx.x >> 7;
+  bool ok;
+  const float* base = raw_base(x1, x2, n, d, inner, row0 + a, ok);
+  float* gbase = ok ? ((row0 + a) < n ? gx1 : gx2) + (base - ((row0 + a) < n ? x1 : x2)) : nullptr;
+  const float inv = ok ? inv_norm[row0 + a] : 0.f;
+  auto load_dz = [&](int c0) {
+    for (int g = threadIdx.x; g < SPCL_TILE * kRawChunk; g += blockDim.x) {
+      const int r = g / kRawChunk, cc = g % kRawChunk;
+      const int64_t gr = row0 + r;
+      tile[cc][r] = (gr < 2 * n && c0 + cc < d) ? dz[gr * lddz + c0 + cc] : 0.f;
+    }
+  };
+  float dot = 0.f;
+  for (int c0 = 0; c0 < d; c0 += kRawChunk) {
+    load_dz(c0);
+    __syncthreads();
+    if (ok)
+      for (int cc = half; cc < kRawChunk && c0 + cc < d; cc += 2)
+        dot = fmaf(base[static_cast<int64_t>(c0 + cc) * inner] * inv, tile[cc][a], dot);
+    __syncthreads();
+  }
+  s_dot[half][a] = dot;
+  __syncthreads();
+  dot = s_dot[0][a] + s_dot[1][a];
+  for (int c0 = 0; c0 < d; c0 += kRawChunk) {
+    load_dz(c0);
+    __syncthreads();
+    if (ok)
+      for (int cc = half; cc < kRawChunk && c0 + cc < d; cc += 2) {
+        const int64_t off = static_cast<int64_t>(c0 + cc) * inner;
+        const float y = base[off] * inv;
+        gbase[off] = inv * (tile[cc][a] - y * dot);
+      }
+    __syncthreads();
+  }
+}
+
 }  // namespace aux
 }  // namespace spcl
 
@@ -446,5 +604,37 @@ extern "C" int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int6
   aux::label_sig_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(labels, n_total, n_blocks,
                                                                             reinterpret_cast<int4*>(sig));
   SPCL_LAUNCH_CHECK("spcl_label_block_sig");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_prepare_raw_bf16(const float* x1, const float* x2, int64_t outer, int64_t d, int64_t inner,
+                                            float eps, const int32_t* labels, void* zb, int64_t n_pad,
+                                            int64_t d_pad, float* inv_norm, int32_t* labels_full, int32_t* sig,
+                                            float* partials, spcl_stream_t stream) {
+  if (x1 == nullptr || x2 == nullptr || zb == nullptr || inv_norm == nullptr || labels_full == nullptr ||
+      sig == nullptr || partials == nullptr || outer <= 0 || d <= 0 || inner <= 0)
+    return SPCL_ERR_INVALID_ARG;
+  const int64_t n = outer * inner;
+  if (d_pad < d || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
+  if (n_pad < 2 * n || n_pad % SPCL_TILE != 0 || n_pad - 2 * n >= SPCL_TILE) return SPCL_ERR_INVALID_ARG;
+  if (!aux::aligned16(zb) || !aux::aligned16(sig)) return SPCL_ERR_INVALID_ARG;
+  aux::prepare_raw_kernel<<<static_cast<unsigned>(n_pad / SPCL_TILE), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x1, x2, n, static_cast<int>(d), inner, eps, labels, static_cast<__nv_bfloat16*>(zb), static_cast<int>(d_pad),
+      inv_norm, labels_full, reinterpret_cast<int4*>(sig), partials);
+  SPCL_LAUNCH_CHECK("spcl_supcon_prepare_raw_bf16");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_raw_bwd(const float* dz, int64_t lddz, const float* x1, const float* x2,
+                                   const float* inv_norm, float* gx1, float* gx2, int64_t outer, int64_t d,
+                                   int64_t inner, spcl_stream_t stream) {
+  if (dz == nullptr || x1 == nullptr || x2 == nullptr || inv_norm == nullptr || gx1 == nullptr || gx2 == nullptr ||
+      outer <= 0 || d <= 0 || inner <= 0 || lddz < d)
+    return SPCL_ERR_INVALID_ARG;
+  const int64_t n = outer * inner;
+  aux::raw_bwd_kernel<<<static_cast<unsigned>(ceil_div(2 * n, static_cast<int64_t>(SPCL_TILE))), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(dz, lddz, x1, x2, inv_norm, gx1, gx2, n,
+                                                             static_cast<int>(d), inner);
+  SPCL_LAUNCH_CHECK("spcl_supcon_raw_bwd");
   return SPCL_OK;
 }

@@ -184,6 +184,40 @@ class _FusedSupConBase(nn.Module):
             raise RuntimeError(loss)
         return loss
 
+    def forward_raw(self, feat1: Tensor, feat2: Tensor, target=None, eps: float = 1e-12):
+        """Loss from UN-normalised projector outputs ``[B, C]`` or ``[B, C, H, W]``: equals
+        ``forward(rows(F.normalize(feat1, dim=1)), rows(F.normalize(feat2, dim=1)), target)`` with ``rows`` the
+        reference's ``[b, c, h, w] -> [b*hw, c]`` reshape (comparable.py:398-404); ``target`` holds one label per
+        anchor (``B`` or ``B*H*W`` entries).  On the tensor-core path the normalise, the reshape copy, the concat
+        and the bf16 pack are one kernel and its backward consumes the loss-gradient rows directly; below the
+        tensor-core threshold (and for ``exclude_other_pos``) it runs the unfused sequence."""
+        assert feat1.shape == feat2.shape and feat1.dim() >= 2, (feat1.shape, feat2.shape)
+        if not (feat1.is_cuda and feat2.is_cuda):
+            raise RuntimeError("spcl_b200 runs on CUDA tensors only: there is no CPU path")
+        outer, d = feat1.shape[0], feat1.shape[1]
+        n = feat1.numel() // d
+        gamma, mode, cg = self._gamma_mode_cg()
+        if not _pick_tc(self._precision, 2 * n, False, int(mode)):
+            def rows(x):
+                y = ops.l2norm_fwd(x.float(), 1, eps)[0]
+                return y.reshape(outer, d, -1).permute(0, 2, 1).reshape(n, d)
+            validate, self._validate = self._validate, False       # normalised by construction
+            try:
+                return self.forward(rows(feat1), rows(feat2), target=target)
+            finally:
+                self._validate = validate
+        dev = feat1.device
+        labels = ops.label_codes(target, n, dev) if target is not None else None
+        scalars, row_stats = ops.supcon_fwd_raw(feat1.float(), feat2.float(), labels, float(self._t), float(gamma),
+                                                int(mode), bool(cg), float(eps))
+        self._scalars = scalars.detach()
+        self._ratio_cache = None
+        self._diag = None                       # the N x N diagnostics need the normalised rows: use forward()
+        loss = scalars[0]
+        if self._check_nan and torch.isnan(loss):
+            raise RuntimeError(loss)
+        return loss
+
     # diagnostics the hooks read after every call; materialised only on access
     def _diag_get(self, name):
         if self._diag is None:

@@ -269,6 +269,69 @@ def supcon_fwd_eager(z1, z2, labels, tri, temperature, gamma, mode, correct_grad
     return _DirectSupCon.apply(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
 
 
+class _RawSupCon(torch.autograd.Function):
+    """Fused projector tail + loss: un-normalised ``[B, C]`` / ``[B, C, H, W]`` projector outputs in,
+    loss out; F.normalize, the NCHW -> [B*HW, C] reshape copy, torch.cat and the bf16 pack are one kernel
+    (``spcl_supcon_prepare_raw_bf16``) and the normalise backward consumes the loss-gradient rows directly
+    (``spcl_supcon_raw_bwd``).  Tensor-core path only."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, labels, temperature, gamma, mode, correct_grad, eps):
+        _require_cuda(x1, x2, labels)
+        if x1.shape != x2.shape or x1.dim() < 2:
+            raise AssertionError((tuple(x1.shape), tuple(x2.shape)))
+        if x1.dtype != torch.float32 or x2.dtype != torch.float32:
+            raise TypeError("the fused projector tail takes float32 projector outputs")
+        x1, x2 = x1.contiguous(), x2.contiguous()
+        outer, d = x1.shape[0], x1.shape[1]
+        inner = math.prod(x1.shape[2:])
+        n = outer * inner
+        N = 2 * n
+        if d > nat.MAX_D:
+            raise nat.SpclError(f"embedding width {d} > {nat.MAX_D} is not supported by this build")
+        if labels is not None and (labels.dtype != torch.int32 or labels.shape != (n,)):
+            raise TypeError("labels must be int32[outer * inner] (one per anchor)")
+        dev, st = x1.device, _stream(x1)
+        n_pad, d_pad = pad_to(N, nat.TILE), pad_to(d, 64)
+        inv_tau = 1.0 / float(temperature)
+        zpack = torch.empty(n_pad, d_pad, dtype=torch.bfloat16, device=dev)
+        labels_full = torch.empty(n_pad, dtype=torch.int32, device=dev)
+        sig = torch.empty(n_pad // nat.TILE, 4, dtype=torch.int32, device=dev)
+        acc = torch.empty(n_pad, 4, dtype=torch.float32, device=dev)
+        row_stats = torch.empty(4, n_pad, dtype=torch.float32, device=dev)
+        partials = torch.empty(3, dtype=torch.float32, device=dev)
+        inv_norm = torch.empty(N, dtype=torch.float32, device=dev)
+        scalars = torch.empty(4, dtype=torch.float32, device=dev)
+        nat.call("spcl_supcon_prepare_raw_bf16", _ptr(x1), _ptr(x2), outer, d, inner, float(eps), _ptr(labels),
+                 _ptr(zpack), n_pad, d_pad, _ptr(inv_norm), _ptr(labels_full), _ptr(sig), _ptr(partials), st)
+        nat.call("spcl_supcon_fwd_bf16", _ptr(zpack), N, n_pad, d_pad, _ptr(labels_full), _ptr(sig), 0, N, inv_tau,
+                 float(gamma), int(mode), _ptr(acc), _ptr(row_stats), _ptr(partials), st)
+        nat.call("spcl_supcon_finalize", _ptr(partials), N, int(bool(correct_grad)), _ptr(scalars), st)
+        ctx.save_for_backward(x1, x2, inv_norm, zpack, labels_full, sig, row_stats, scalars)
+        ctx.hp = (float(temperature), float(gamma), int(mode), n, d, outer, inner)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(row_stats)
+        return scalars, row_stats
+
+    @staticmethod
+    def backward(ctx, g_scalars, _g_stats):
+        if g_scalars is None:
+            return (None,) * 8
+        x1, x2, inv_norm, zpack, labels_full, sig, row_stats, scalars = ctx.saved_tensors
+        temperature, gamma, mode, n, d, outer, inner = ctx.hp
+        dz = supcon_bwd._init_fn(g_scalars[0], zpack, labels_full, sig, None, row_stats, scalars, temperature, gamma,
+                                 mode, True, n, d)
+        gx1, gx2 = torch.empty_like(x1), torch.empty_like(x2)
+        nat.call("spcl_supcon_raw_bwd", _ptr(dz), dz.stride(0), _ptr(x1), _ptr(x2), _ptr(inv_norm), _ptr(gx1),
+                 _ptr(gx2), outer, d, inner, _stream(x1))
+        return gx1, gx2, None, None, None, None, None, None
+
+
+def supcon_fwd_raw(x1, x2, labels, temperature, gamma, mode, correct_grad, eps=1e-12):
+    """-> (scalars[4], row_stats) from UN-normalised projector outputs ``[B, C]`` or ``[B, C, *spatial]``."""
+    return _RawSupCon.apply(x1, x2, labels, temperature, gamma, mode, correct_grad, eps)
+
+
 class GraphRunner:
     """fwd + bwd of one loss call as ONE CUDA-graph replay, for fixed (n, d) and hyper-parameters.
 
