@@ -323,6 +323,40 @@ def main():
            "serial_ms_per_step": serial_s * 1e3, "serial_value": N * N / serial_s, "h2d_only_ms": h2d_ms,
            "h2d_bytes_per_step": feed.h2d_bytes // e2e_steps, "d2h_bytes_per_step": 4}
 
+    # ---------------- the reference's own batch size (cfg2), secondary figure ----------------
+    # K = 3 meta-label problems of 2 x 256 anchors, d = 256 (encoder pre-training) through the public
+    # modules: fwd + bwd of all three, eager launches vs cuda_graph=True (one graph replay per loss call).
+    small = None
+    if world == 1:
+        from spcl_b200.workloads import acdc_meta_labels, make_views
+        meta = acdc_meta_labels(256)
+        def small_step(graphed):
+            probs = []
+            for kind, gm in (("partition", 5.0), ("patient", 3.5), ("cycle", 2.0)):
+                c = spcl_b200.SelfPacedSupConLoss(weight_update="soft", correct_grad=True, check_nan=False,
+                                                  validate=False, cuda_graph=graphed)
+                c.set_gamma(gm)
+                v1, v2 = make_views(meta[kind], 256, sigma=0.7, seed=1)
+                probs.append((c, v1.to(dev).requires_grad_(True), v2.to(dev).requires_grad_(True),
+                              meta[kind].int().to(dev)))
+            def run():
+                tot = None
+                for c, p1, p2, lb in probs:
+                    p1.grad = p2.grad = None
+                    l = c(p1, p2, target=lb)
+                    tot = l if tot is None else tot + l
+                tot.backward()
+            for _ in range(10):
+                run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                run()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / 100 * 1e6
+        small = {"workload": "cfg2: 3 meta-label problems, N = 512, d = 256, fp32 path, fwd+bwd of all three",
+                 "eager_us_per_step": small_step(False), "cuda_graph_us_per_step": small_step(True)}
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
@@ -338,7 +372,7 @@ def main():
             "config": {"workload": workload, "anchors_N": N, "d": d, "rows_per_gpu": rows,
                        "hyper": {"tau": TAU, "gamma": GAMMA, "mode": MODE_NAME, "labels": spec["labels"]},
                        "l2": "256 MB flush between timed steps", "parallelism": f"row-shard x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 6 * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "small_batch": small, "gpu_launches": 6 * args.steps,
             "clocks": clocks, "loss": loss_val,
         }
         print(json.dumps(line), flush=True)
