@@ -90,6 +90,7 @@ struct Params {
   // symmetric pass split over ranks: this launch is CTAs [vblock0, vblock0 + gridDim.x) of a virtual grid of
   // vgrid CTAs that together cover the triangle (vgrid == 0: the launch is the whole grid)
   unsigned vgrid, vblock0;
+  int sig_smem;                // sp pass: the signature table (16 B per 128 anchors) is staged in shared memory
 };
 
 // debug timeline: trace[((role * 64 + tile) * 4 + event)] = clock64() for the first 64 tiles of CTA 0
@@ -275,11 +276,11 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 // tiles whose label signature can match the row block's; 32 candidates are tested per step (one per lane)
 // so the scan costs one L2 round trip per 32 tiles instead of one per tile.
 template <typename F>
-__device__ __forceinline__ void for_each_pos_tile(const Params& p, const int4& rsig, int64_t tb, int64_t te, int lane,
-                                                  F&& f) {
+__device__ __forceinline__ void for_each_pos_tile(const int4* __restrict__ sigt, const int4& rsig, int64_t tb,
+                                                  int64_t te, int lane, F&& f) {
   for (int64_t base = tb; base < te; base += 32) {
     const int64_t t = base + lane;
-    const bool act = (t < te) && sig_overlap(rsig, p.sig[t]);
+    const bool act = (t < te) && sig_overlap(rsig, sigt[t]);
     unsigned m = __ballot_sync(kFullMask, act);
     while (m) {
       const int b = __ffs(m) - 1;
@@ -385,21 +386,17 @@ __device__ __forceinline__ void stats_chunk_fast(const uint32_t (&v)[32], const 
   }
 }
 
-// slow: diagonal / tail / tiles that may hold positives.  jdiag = column of this row's diagonal element inside
-// the 128-column block (or -1), jmax = number of valid columns, lab = labels of the block's columns (global).
-__device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
-                                                 const int32_t* __restrict__ lab, float c2, float& rowsum,
-                                                 float& cnt, float& spx) {
+// slow: the diagonal block and the tail block.  jdiag = column of this row's diagonal element inside the
+// 128-column block (or -1), jmax = number of valid columns.  (Positives are ordinary members of the row sum; they are
+// counted by the sp pass, which visits exactly the tiles that can hold them.)
+__device__ __forceinline__ void stats_chunk_slow(const uint32_t (&v)[32], int ch, int jdiag, int jmax, float c2,
+                                                 float& rowsum) {
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
     const int cidx = ch * 32 + e;
-    const float dot = __uint_as_float(v[e]);
     const bool valid = (cidx < jmax) && (cidx != jdiag);
-    const bool pos = valid && (__ldg(lab + cidx) == li);
-    const float ex = ex2_approx(fmaf(dot, c2, -c2));
+    const float ex = ex2_approx(fmaf(__uint_as_float(v[e]), c2, -c2));
     rowsum += valid ? ex : 0.f;
-    cnt += pos ? 1.f : 0.f;
-    spx += pos ? dot : 0.f;
   }
 }
 
@@ -475,56 +472,41 @@ __device__ __forceinline__ void sym_col_flush(uint64_t (&k0)[4], const uint64_t 
   for (int ch = 0; ch < 4; ++ch) atomicAdd(colacc + ch * 32 * 4, out[ch]);
 }
 
-// slow + column sums (tiles right of the diagonal that may hold positives, tail block): 32x32b layout, this
-// thread = one row.  Column `lane` of the chunk gets its three sums over the warp's rows, accumulated into the
-// mirrored rows' acc entries.
-__device__ __forceinline__ void stats_chunk_slow_sym(const uint32_t (&v)[32], int ch, int jmax, int li, bool row_ok,
-                                                     const int32_t* __restrict__ lab, float c2, bool want_spx,
-                                                     float4* __restrict__ acc_cols, int lane, float& rowsum,
-                                                     float& cnt, float& spx) {
-  float ev[32], pv[32];
+// slow + column sums (the tail block right of the diagonal): 32x32b layout, this thread = one row.  Column `lane`
+// of the chunk gets its sum over the warp's rows, accumulated into the mirrored row's acc entry.
+__device__ __forceinline__ void stats_chunk_slow_sym(const uint32_t (&v)[32], int ch, int jmax, bool row_ok, float c2,
+                                                     float4* __restrict__ acc_cols, int lane, float& rowsum) {
+  float ev[32];
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
-    const int cidx = ch * 32 + e;
-    const float dot = __uint_as_float(v[e]);
-    const bool valid = cidx < jmax;                 // no diagonal right of the diagonal block
-    const bool pos = valid && (__ldg(lab + cidx) == li);
-    const float ex = ex2_approx(fmaf(dot, c2, -c2));
+    const bool valid = (ch * 32 + e) < jmax;        // no diagonal right of the diagonal block
+    const float ex = ex2_approx(fmaf(__uint_as_float(v[e]), c2, -c2));
     rowsum += valid ? ex : 0.f;
-    cnt += pos ? 1.f : 0.f;
-    spx += pos ? dot : 0.f;
     ev[e] = (valid && row_ok) ? ex : 0.f;
-    pv[e] = (pos && row_ok) ? 1.f : 0.f;
   }
   const float ce = warp_colsum32(ev, lane);
-  const float cp = warp_colsum32(pv, lane);
-  float* a = reinterpret_cast<float*>(acc_cols + ch * 32 + lane);
-  if (ce != 0.f) atomicAdd(a + 0, ce);
-  if (cp != 0.f) atomicAdd(a + 1, cp);
-  if (want_spx && __any_sync(kFullMask, cp != 0.f)) {      // warp-uniform: the butterfly needs every lane
-    float dv[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const int cidx = ch * 32 + e;
-      const bool pos = row_ok && (cidx < jmax) && (__ldg(lab + cidx) == li);
-      dv[e] = pos ? __uint_as_float(v[e]) : 0.f;
-    }
-    const float cd = warp_colsum32(dv, lane);
-    if (cd != 0.f) atomicAdd(a + 2, cd);
-  }
+  if (ce != 0.f) atomicAdd(reinterpret_cast<float*>(acc_cols + ch * 32 + lane), ce);
 }
 
+// sp pass: positives of this row in 32 columns.  cnt += P;  NONE: wl += P <z_i, z_j>;  hard / soft: wl += P W LLH,
+// wp += P W with W from the final logD_i.
 __device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
-                                         const int32_t* lab_s, const Params& p, float logD, float& wl, float& wp) {
+                                         const int32_t* lab_s, const Params& p, float logD, float& wl, float& wp,
+                                         float& cnt) {
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
     const int cidx = ch * 32 + e;
     const float dot = __uint_as_float(v[e]);
     const bool pos = (cidx < jmax) && (cidx != jdiag) && (lab_s[cidx] == li);
-    const float l = fmaf(-dot, p.inv_tau, logD);          // l_ij = logD_i - S_ij
-    const float w = pos ? sp_weight(l, p.gamma, p.inv_gamma, p.mode) : 0.f;
-    wl = fmaf(w, -l, wl);
-    wp += w;
+    cnt += pos ? 1.f : 0.f;
+    if (p.mode == SPCL_MODE_NONE) {
+      wl += pos ? dot : 0.f;
+    } else {
+      const float l = fmaf(-dot, p.inv_tau, logD);          // l_ij = logD_i - S_ij
+      const float w = pos ? sp_weight(l, p.gamma, p.inv_gamma, p.mode) : 0.f;
+      wl = fmaf(w, -l, wl);
+      wp += w;
+    }
   }
 }
 
@@ -616,7 +598,6 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
 
   const CtaRange range = cta_range_of(p, BN);
   constexpr int kSymShift = SYM ? (kSub == 2 ? 1 : 0) : -1;
-  const int64_t rb0 = p.row_begin / TILE;
   const uint32_t a_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
   const uint32_t slot_tx = static_cast<uint32_t>(p.dc) * BN * 128;
 
@@ -691,29 +672,18 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
     const ExpK ek = make_expk<4>(p);
     int64_t gi0 = 0, gi = 0;
     bool row_ok = false;
-    int li = 0;
-    int4 rsig = make_int4(0, 0, 0, 0);
     uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};       // fast path: packed partial row sums (SYM: one per held row)
-    float s0 = 0.f, cnt = 0.f, spx = 0.f;              // slow path: rowsum, positives, sum P dot
+    float s0 = 0.f;                                    // slow path: rowsum
     // SYM fast path: column this lane ends up with after the butterfly, row it flushes at the end of a segment
     const int sym_col = (lane & 16) + (lane & 8) + 2 * (lane & 3) + ((lane >> 2) & 1);
     const int sym_row = q * 32 + 16 * ((lane >> 1) & 1) + 8 * (lane & 1) + (lane >> 2);
 
-    // Which tiles need the generic path (diagonal, tail, possible positives) is decided for 32 column tiles at a
-    // time, one tile per lane, and kept as a warp-uniform bit mask: with two warps per scheduler every
-    // bookkeeping instruction between two tiles costs 10+ exposed cycles, and per-tile signature loads with
-    // 64-bit index math were ~1000 cycles in front of ~2000 cycles of arithmetic.
+    // Only the diagonal block (exclude j == i) and the tail block (j < N) need the generic path: every other
+    // element -- positives included -- is a plain member of the row sum.  Labels are not read here at all.
     const uint32_t ct128 = static_cast<uint32_t>(p.CT128);
     const uint32_t tail_jb = (p.N % TILE) ? ct128 - 1u : 0xffffffffu;   // block that needs the j < N mask
     uint32_t row_jb = 0;                                                // block that holds this row block's diagonal
     auto block_of = [&](uint32_t t) -> uint32_t { return t * kSub + (kSub == 2 ? static_cast<uint32_t>(wg) : 0u); };
-    auto slow_mask = [&](uint32_t grp) -> uint32_t {
-      const uint32_t jb = block_of((grp << 5) + static_cast<uint32_t>(lane));
-      bool slow = true;
-      if (jb < ct128) slow = jb == row_jb || jb == tail_jb || sig_overlap(rsig, p.sig[jb]);
-      return __ballot_sync(kFullMask, slow);
-    };
-    uint32_t mask = 0, mask_grp = 0xffffffffu;
     Ring rb(kBufs);
     for (TileCursor c(range, p.CT, p.RB, kSymShift); c.valid(); c.next(), rb.next()) {
       if (c.first()) {
@@ -721,20 +691,13 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
         gi = gi0 + r;
         row_jb = static_cast<uint32_t>(gi0 / TILE);
         row_ok = gi < p.row_end;
-        li = row_ok ? p.labels[gi] : 0;
-        rsig = p.sig[rb0 + c.I];
-        mask_grp = 0xffffffffu;
       }
       const bool mine = (kSub == 2) || (static_cast<int>(c.it % NWG) == wg);
       if (mine) {
         const int buf = rb.idx;
         const uint32_t bph = rb.ph;
-        if ((c.t >> 5) != mask_grp) {
-          mask_grp = c.t >> 5;
-          mask = slow_mask(mask_grp);
-        }
-        const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u && !(p.dbg & 1024);   // 1024: timing experiment
         const uint32_t jb = block_of(c.t);
+        const bool slow = (jb == row_jb || jb == tail_jb) && !(p.dbg & 1024);     // 1024: timing experiment
         const int64_t j0 = static_cast<int64_t>(jb) * TILE;
         const bool inside = jb < ct128 && !(SYM && jb < row_jb);
         const bool cols = SYM && (jb > row_jb || (p.dbg & 1024));
@@ -766,7 +729,6 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
             const int64_t dj = gi - j0;
             const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
             const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
-            const int32_t* lab = p.labels + j0;
             uint32_t va[32], vb[32];
             tmem_ld_32x32b_x32(taddr, va);
             tmem_wait_ld();
@@ -776,11 +738,9 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
               uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
               if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);     // in flight during the math below
               if (p.dbg & 1) acc2[ch] ^= cur[ch];
-              else if (SYM && cols)
-                stats_chunk_slow_sym(cur, ch, jmax, li, row_ok, lab, p.c2, p.mode == SPCL_MODE_NONE, p.acc + j0, lane,
-                                     s0, cnt, spx);
+              else if (SYM && cols) stats_chunk_slow_sym(cur, ch, jmax, row_ok, p.c2, p.acc + j0, lane, s0);
               else if (!SYM && !slow) stats_chunk_fast(cur, ek, acc2);
-              else stats_chunk_slow(cur, ch, jdiag, jmax, li, lab, p.c2, s0, cnt, spx);
+              else stats_chunk_slow(cur, ch, jdiag, jmax, p.c2, s0);
               if (ch < 3) tmem_wait_ld();
             }
           }
@@ -818,12 +778,10 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
             }
           }
           if (rowsum != 0.f) atomicAdd(a + 0, rowsum);
-          if (cnt != 0.f) atomicAdd(a + 1, cnt);
-          if (p.mode == SPCL_MODE_NONE && spx != 0.f) atomicAdd(a + 2, spx);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc2[k] = 0ull;
-        s0 = cnt = spx = 0.f;
+        s0 = 0.f;
       }
     }
   }
@@ -848,6 +806,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
   if (warp == kMmaWarp0 && lane == 0) init_barriers(bar, /*slot: MMA commit + 4 epilogue warps*/ 5, 4, /*a_empty*/ 2);
   if (warp == kAllocWarp) tmem_alloc<kTmemCols>(&bar->tmem_base);
   if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tmap);
+  // every role scans the signature table once per row block (32 tiles per step): from shared memory when it fits
+  // -- from L2 the scan was ~5000 cycles per row block and most of this kernel's time at cfg3
+  const int4* sigt = p.sig;
+  if (p.sig_smem) {
+    int4* s_sig = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(bar) + ((sizeof(Barriers) + 15) & ~size_t(15)));
+    for (int64_t t = threadIdx.x; t < p.CT; t += blockDim.x) s_sig[t] = p.sig[t];
+    sigt = s_sig;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -871,8 +837,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
         mbar_arrive_expect_tx(&bar->a_full, static_cast<uint32_t>(p.dc) * CHUNK_BYTES);
         for (int c = 0; c < p.dc; ++c) tma_load_2d(sm.a_tile + c * CHUNK_BYTES, &tmap, &bar->a_full, c * 64, gi0);
       }
-      const int4 rsig = p.sig[rb0 + I];
-      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t t) {
+      const int4 rsig = sigt[rb0 + I];
+      for_each_pos_tile(sigt, rsig, tb, te, lane, [&](int64_t t) {
         if (lane == 0) {
           const int slot = it % p.nslot;
           const uint32_t ph = (it / p.nslot) & 1;
@@ -899,8 +865,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
       f += te - tb;
       if (lane == 0) mbar_wait(&bar->a_full, seg & 1);
       __syncwarp();
-      const int4 rsig = p.sig[rb0 + I];
-      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t) {
+      const int4 rsig = sigt[rb0 + I];
+      for_each_pos_tile(sigt, rsig, tb, te, lane, [&](int64_t) {
         if ((it & 1) == mw) {
           const int slot = it % p.nslot, buf = it % p.nbuf;
           const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
@@ -935,12 +901,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
       const int64_t gi = gi0 + r;
       const bool row_ok = gi < p.row_end;
       const int li = row_ok ? p.labels[gi] : 0;
-      const int4 rsig = p.sig[rb0 + I];
+      const int4 rsig = sigt[rb0 + I];
       float logD = 0.f;
       if (row_ok) logD = p.inv_tau + logf(p.acc[gi].x);
-      float s0 = 0.f, s1 = 0.f;                          // wl, wp
+      float s0 = 0.f, s1 = 0.f, cnt = 0.f;               // wl (NONE: sum P dot), wp, number of positives
 
-      for_each_pos_tile(p, rsig, tb, te, lane, [&](int64_t t) {
+      for_each_pos_tile(sigt, rsig, tb, te, lane, [&](int64_t t) {
         const bool mine = static_cast<int>(it & 1) == wg;
         if (mine) {
           const int slot = it % p.nslot, buf = it % p.nbuf;
@@ -965,7 +931,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
             uint32_t(&cur)[32] = (ch & 1) ? vb : va;
             uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
             if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
-            sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1);
+            sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
             if (ch < 3) tmem_wait_ld();
           }
           tc_fence_before();
@@ -978,10 +944,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
         ++it;
       });
 
-      if (row_ok && s1 != 0.f) {
+      if (row_ok && cnt != 0.f) {
         float* a = reinterpret_cast<float*>(p.acc + gi);
-        atomicAdd(a + 2, s0);
-        atomicAdd(a + 3, s1);
+        atomicAdd(a + 1, cnt);
+        if (p.mode == SPCL_MODE_NONE || s1 != 0.f) atomicAdd(a + 2, s0);
+        if (s1 != 0.f) atomicAdd(a + 3, s1);
       }
     }
   }
@@ -1810,11 +1777,15 @@ static int launch_stats(const tc::Params& p, const void* zb, int64_t n_pad, int3
 static int launch_finish(const tc::Params& p, int64_t n_pad, int64_t row_begin, int64_t row_end, float inv_tau,
                          int mode, float* row_stats, float* partials, const CUtensorMap& tmap128, cudaStream_t s) {
   int rc = SPCL_OK;
-  if (mode != SPCL_MODE_NONE) {
+  {
+    // every mode: this pass also counts the positives (and, for W == 1, sums their similarities)
     tc::Params pb = p;
     pb.nslot = tc::pick_slots(p.dc, 128, true);
     pb.nbuf = tc::kMaxBufs;
-    const size_t smem = tc::smem_payload_bytes(pb.dc, pb.nslot, 128, true) + 1024;
+    const size_t sig_bytes = p.CT128 <= 2048 ? static_cast<size_t>(p.CT128) * 16 + 16 : 0;
+    pb.sig_smem = sig_bytes != 0;
+    while (pb.nslot > 2 && tc::smem_payload_bytes(pb.dc, pb.nslot, 128, true) + 1024 + sig_bytes > 226 * 1024) --pb.nslot;
+    const size_t smem = tc::smem_payload_bytes(pb.dc, pb.nslot, 128, true) + 1024 + sig_bytes;
     rc = tc::set_smem(tc::sp_kernel, smem);
     if (rc != SPCL_OK) return rc;
     tc::sp_kernel<<<tc::grid_for(pb), tc::NTHREADS, smem, s>>>(tmap128, pb);

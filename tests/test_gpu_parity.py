@@ -389,10 +389,11 @@ def test_hostfeed_matches_direct_calls():
         feed.release(slot, loss)
     got = feed.losses()
     assert feed.h2d_bytes == steps * (2 * n * d * 4 + n * 4)
-    np.testing.assert_allclose(got, want, rtol=1e-6)
+    np.testing.assert_allclose(got, want, rtol=1e-5)
     for g, w in zip(got_g, want_g):
-        # dZ is accumulated with atomics: same terms, different order
-        assert (g - w).abs().max().item() <= 1e-5 * w.abs().max().item()
+        # row sums and dZ are accumulated with atomics: same terms, different order; a last-bit change of a row
+        # statistic can flip the bf16 rounding of a T element (2^-9 of that element)
+        assert (g - w).abs().max().item() <= 2e-4 * w.abs().max().item()
     with pytest.raises(RuntimeError):
         for _ in range(3):
             feed.push(*pinned[0], lab_h)
