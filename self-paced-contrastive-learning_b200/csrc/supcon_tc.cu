@@ -191,9 +191,25 @@ struct CtaRange {
   uint32_t t0, n;    // first column tile inside it, number of tiles
 };
 
-__device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
+// CTA vb of vg (virtual grid) of the symmetric pass: equal contiguous cut of the folded tile list
+__host__ __device__ inline CtaRange sym_range(int64_t RB, int64_t CT, int bn, int64_t vb, int64_t vg) {
   CtaRange r;
+  const int64_t total = sym_prefix(RB, CT, bn);
+  const int64_t f0 = total * vb / vg, f1 = total * (vb + 1) / vg;
+  int64_t lo = 0, hi = RB - 1;                 // largest o with sym_fold_prefix(o) <= f0
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (sym_fold_prefix(mid, RB, CT, bn) <= f0) lo = mid; else hi = mid - 1;
+  }
+  r.I0 = lo;
+  r.t0 = static_cast<uint32_t>(sym_first_tile(sym_fold(lo, RB), bn) + (f0 - sym_fold_prefix(lo, RB, CT, bn)));
+  r.n = static_cast<uint32_t>(f1 - f0);
+  return r;
+}
+
+__device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
   if (!p.sym) {
+    CtaRange r;
     int64_t f0, f1;
     cta_range(p, f0, f1);
     r.I0 = f0 / p.CT;
@@ -201,18 +217,7 @@ __device__ __forceinline__ CtaRange cta_range_of(const Params& p, int bn) {
     r.n = static_cast<uint32_t>(f1 - f0);
     return r;
   }
-  const int64_t total = sym_prefix(p.RB, p.CT, bn);
-  const int64_t vb = p.vgrid ? p.vblock0 + blockIdx.x : blockIdx.x, vg = p.vgrid ? p.vgrid : gridDim.x;
-  const int64_t f0 = total * vb / vg, f1 = total * (vb + 1) / vg;
-  int64_t lo = 0, hi = p.RB - 1;                 // largest o with sym_fold_prefix(o) <= f0
-  while (lo < hi) {
-    const int64_t mid = (lo + hi + 1) >> 1;
-    if (sym_fold_prefix(mid, p.RB, p.CT, bn) <= f0) lo = mid; else hi = mid - 1;
-  }
-  r.I0 = lo;
-  r.t0 = static_cast<uint32_t>(sym_first_tile(sym_fold(lo, p.RB), bn) + (f0 - sym_fold_prefix(lo, p.RB, p.CT, bn)));
-  r.n = static_cast<uint32_t>(f1 - f0);
-  return r;
+  return sym_range(p.RB, p.CT, bn, p.vgrid ? p.vblock0 + blockIdx.x : blockIdx.x, p.vgrid ? p.vgrid : gridDim.x);
 }
 
 // Walks the CTA's flattened tile range one tile at a time; a "segment" is the part of one row block.
@@ -222,10 +227,10 @@ struct TileCursor {
   uint32_t I;        // current row block (relative to row_begin)
   uint32_t o, RB;    // symmetric: position in the folded order, number of row blocks
   int symshift;      // < 0: every row block starts at tile 0; else row block I starts at tile I >> symshift
-  __device__ __forceinline__ TileCursor(int64_t f0, int64_t f1, int64_t ct)
+  __host__ __device__ __forceinline__ TileCursor(int64_t f0, int64_t f1, int64_t ct)
       : t(static_cast<uint32_t>(f0 % ct)), CT(static_cast<uint32_t>(ct)), it(0), n(static_cast<uint32_t>(f1 - f0)),
         seg(0), tfirst(0), I(static_cast<uint32_t>(f0 / ct)), o(0), RB(0), symshift(-1) {}
-  __device__ __forceinline__ TileCursor(const CtaRange& r, int64_t ct, int64_t rb, int symshift_)
+  __host__ __device__ __forceinline__ TileCursor(const CtaRange& r, int64_t ct, int64_t rb, int symshift_)
       : t(r.t0), CT(static_cast<uint32_t>(ct)), it(0), n(r.n), seg(0), tfirst(0), I(static_cast<uint32_t>(r.I0)),
         o(static_cast<uint32_t>(r.I0)), RB(static_cast<uint32_t>(rb)), symshift(symshift_) {
     if (symshift >= 0) {
@@ -233,10 +238,10 @@ struct TileCursor {
       tfirst = I >> symshift;
     }
   }
-  __device__ __forceinline__ bool valid() const { return it < n; }
-  __device__ __forceinline__ bool first() const { return it == 0 || t == tfirst; }
-  __device__ __forceinline__ bool last() const { return it + 1 == n || t + 1 == CT; }
-  __device__ __forceinline__ void next() {
+  __host__ __device__ __forceinline__ bool valid() const { return it < n; }
+  __host__ __device__ __forceinline__ bool first() const { return it == 0 || t == tfirst; }
+  __host__ __device__ __forceinline__ bool last() const { return it + 1 == n || t + 1 == CT; }
+  __host__ __device__ __forceinline__ void next() {
     if (last()) ++seg;
     ++it;
     if (++t == CT) {
@@ -1933,4 +1938,23 @@ extern "C" int spcl_debug_set_flags(int flags) {
 extern "C" int spcl_debug_set_trace(void* buf) {
   tc::g_trace = static_cast<unsigned long long*>(buf);
   return SPCL_OK;
+}
+
+// debug / test only (not part of include/spcl.h): the tiles CTA vb of vg visits in the symmetric pass, produced by
+// the SAME range and cursor code the kernel runs.  out: up to `cap` (row block, column tile, first, last) quadruples;
+// returns the number of tiles of the range.
+extern "C" int64_t spcl_debug_sym_walk(int64_t RB, int64_t CT, int bn, int64_t vb, int64_t vg, int32_t* out,
+                                       int64_t cap) {
+  if (RB <= 0 || CT <= 0 || (bn != 128 && bn != 256) || vg <= 0 || vb < 0 || vb >= vg) return -1;
+  const tc::CtaRange r = tc::sym_range(RB, CT, bn, vb, vg);
+  int64_t k = 0;
+  for (tc::TileCursor c(r, CT, RB, bn == 256 ? 1 : 0); c.valid(); c.next(), ++k) {
+    if (k < cap) {
+      out[4 * k + 0] = static_cast<int32_t>(c.I);
+      out[4 * k + 1] = static_cast<int32_t>(c.t);
+      out[4 * k + 2] = c.first() ? 1 : 0;
+      out[4 * k + 3] = c.last() ? 1 : 0;
+    }
+  }
+  return k;
 }

@@ -146,3 +146,40 @@ def test_workload_shapes():
     assert z1.shape == (64, 128) and lab.shape == (64,)
     assert torch.allclose(z1.norm(dim=1), torch.ones(64), atol=1e-5)
     assert set(WORKLOADS) >= {"cfg2_encoder_2x256_d256", "cfg3_dense_2x16384_d128_simclr"}
+
+
+# ---- symmetric pass A: the tile enumeration the kernel walks (host copy of the same code) --------------------
+@pytest.mark.parametrize("RB,bn", [(1, 256), (2, 256), (3, 128), (5, 256), (8, 128), (16, 256), (37, 256), (64, 128),
+                                   (256, 256), (255, 256)])
+@pytest.mark.parametrize("vg", [1, 2, 7, 148, 296])
+def test_symmetric_tile_walk_covers_the_triangle_exactly_once(RB, bn, vg):
+    """Every (row block I, column tile t >= first tile of I) is visited by exactly one CTA of the (virtual) grid --
+    also when the grid is the concatenation of several ranks' launches -- ranges are balanced to one tile, and the
+    segment flags (`first` / `last`: A-tile reload, row flush) bracket each row-block segment of a CTA."""
+    h = nat.lib()
+    h.spcl_debug_sym_walk.restype = ctypes.c_int64
+    h.spcl_debug_sym_walk.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_int64]
+    per128 = bn // 128
+    CT = -(-RB // per128)
+    want = {(I, t) for I in range(RB) for t in range(I // per128, CT)}
+    seen = {}
+    counts = []
+    cap = len(want) + 8
+    buf = np.zeros((cap, 4), dtype=np.int32)
+    for vb in range(vg):
+        k = h.spcl_debug_sym_walk(RB, CT, bn, vb, vg, buf.ctypes.data_as(ctypes.c_void_p), cap)
+        assert 0 <= k <= cap
+        counts.append(k)
+        tiles = buf[:k].copy()
+        for idx, (I, t, first, last) in enumerate(tiles):
+            assert (I, t) not in seen, f"tile {(I, t)} visited by CTA {seen.get((I, t))} and {vb}"
+            seen[(int(I), int(t))] = vb
+            starts = idx == 0 or tiles[idx - 1][0] != I
+            ends = idx == k - 1 or tiles[idx + 1][0] != I
+            assert bool(first) == starts and bool(last) == ends, (vb, idx, I, t, first, last)
+            if not starts:
+                assert t == tiles[idx - 1][1] + 1          # consecutive column tiles inside a segment
+    assert set(seen) == want
+    assert max(counts) - min(counts) <= 1
+    assert h.spcl_debug_sym_walk(RB, CT, bn, vg, vg, None, 0) == -1        # vb out of range
