@@ -103,6 +103,25 @@ int spcl_supcon_prepare_raw_bf16(const float* x1, const float* x2, int64_t outer
 int spcl_supcon_raw_bwd(const float* dz, int64_t lddz, const float* x1, const float* x2, const float* inv_norm,
                         float* gx1, float* gx2, int64_t outer, int64_t d, int64_t inner, spcl_stream_t stream);
 
+/* ---- dense-contrast front end -----------------------------------------------------
+ * The tail of DenseProjectionHead (contrastyou/projectors/heads.py:109-115: AdaptiveAvgPool2d(spatial_size), then
+ * F.normalize(dim=1)) followed by either the dense hook's point sampling (region_extractor,
+ * semi_seg/hooks/infonce.py:233-241) or the all-pixels reshape [b,c,h,w] -> [b*h*w, c]
+ * (contrastyou/epocher/comparable.py:398-404), in one pass over the projector output x: float [B][C][H][W].
+ *   points == NULL: every pooled pixel, P = ph*pw, row (b*ph + i)*pw + j.
+ *   points != NULL: int32 [B*P], points[b*P + p] = i*pw + j in the pooled grid (0 <= value < ph*pw, checked by the
+ *                   caller); only those windows are read.  Row b*P + p.
+ * y: float [B*P][C] unit rows, inv_norm: float [B*P] = 1 / max(||pooled||, eps).  ph <= H and pw <= W
+ * (SPCL_ERR_UNSUPPORTED otherwise; the reference only pools down). */
+int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
+                        int64_t ph, int64_t pw, int64_t P, float eps, float* y, float* inv_norm,
+                        spcl_stream_t stream);
+/* backward of the pooling / gather: g_pooled float [B*P][C] is the gradient with respect to the pooled
+ * (un-normalised) rows -- spcl_l2norm_bwd(gy, y, inv_norm, inner = 1) produces it -- and gx: float [B][C][H][W]
+ * is fully written (zeros outside the sampled windows). */
+int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
+                        int64_t ph, int64_t pw, int64_t P, float* gx, spcl_stream_t stream);
+
 /* per-128-anchor label signatures used to skip tiles without positives: int32[n_pad/128][4] */
 int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
                          spcl_stream_t stream);

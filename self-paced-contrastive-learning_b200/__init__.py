@@ -6,11 +6,13 @@ and the projector's L2-normalise tail) as hand-written sm_100a CUDA kernels behi
 """
 from . import _native
 from ._native import LIB_PATH, SpclError, build
+from . import dense, hooks
+from .dense import DenseProjectionTail, point_coordinates, region_extractor
 from .hostfeed import HostFeed
 from .losses import SelfPacedSupConLoss, SupConLoss1, is_normalized, supcon_loss
 from .projectors import Normalize, normalize
 from .schedule import PScheduler
 
 __all__ = ["SelfPacedSupConLoss", "SupConLoss1", "supcon_loss", "is_normalized", "Normalize", "normalize",
-           "PScheduler", "HostFeed", "build", "LIB_PATH", "SpclError"]
+           "PScheduler", "HostFeed", "DenseProjectionTail", "point_coordinates", "region_extractor", "dense", "hooks", "build", "LIB_PATH", "SpclError"]
 __version__ = "0.1.0"

@@ -466,3 +466,69 @@ def _l2_backward(ctx, gy, g_inv):
 
 
 l2norm_fwd.register_autograd(_l2_backward, setup_context=_l2_setup)
+
+
+# --------------------------------------------------------------------------------------------------
+# dense-contrast front end: pool + normalise + point gather / rows reshape in one pass
+# --------------------------------------------------------------------------------------------------
+class _DenseRows(torch.autograd.Function):
+    """x [B, C, H, W] fp32 -> unit rows [B*P, C] (heads.py:109-115 + infonce.py:233-241 / comparable.py:398-404)."""
+
+    @staticmethod
+    def forward(ctx, x, points, ph, pw, eps):
+        _require_cuda(x, points)
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        P = ph * pw if points is None else points.shape[1]
+        y = torch.empty(B * P, C, dtype=torch.float32, device=x.device)
+        inv = torch.empty(B * P, dtype=torch.float32, device=x.device)
+        if y.numel():
+            nat.call("spcl_dense_rows_fwd", _ptr(x), _ptr(points), B, C, H, W, ph, pw, P, float(eps), _ptr(y),
+                     _ptr(inv), _stream(x))
+        ctx.save_for_backward(y, inv, points)
+        ctx.geom = (B, C, H, W, ph, pw, P)
+        ctx.mark_non_differentiable(inv)
+        return y, inv
+
+    @staticmethod
+    def backward(ctx, gy, _g_inv):
+        if gy is None:
+            return None, None, None, None, None
+        y, inv, points = ctx.saved_tensors
+        B, C, H, W, ph, pw, P = ctx.geom
+        g_pooled = l2norm_bwd(gy.float(), y, inv, 1)            # rows layout: d(loss)/d(pooled value)
+        gx = torch.empty(B, C, H, W, dtype=torch.float32, device=y.device)
+        if gx.numel():
+            nat.call("spcl_dense_rows_bwd", _ptr(g_pooled), _ptr(points), B, C, H, W, ph, pw, P, _ptr(gx),
+                     _stream(y))
+        return gx, None, None, None, None
+
+
+def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: float = 1e-12) -> Tensor:
+    """Unit-norm anchor rows from a dense projector output.
+
+    ``x``: ``[B, C, H, W]`` (any float dtype; computed in fp32).  ``spatial_size``: the adaptive-average-pool
+    target ``(ph, pw)`` (``None`` = no pooling).  ``points``: ``None`` for every pooled pixel (rows ordered
+    ``(b, i, j)``) or an integer tensor ``[B, P]`` of flat pooled coordinates ``i * pw + j`` (rows ordered
+    ``(b, p)``).  Differentiable with respect to ``x``."""
+    if x.dim() != 4:
+        raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
+    _require_cuda(x)
+    H, W = x.shape[2:]
+    if spatial_size is None:
+        ph, pw = H, W
+    elif isinstance(spatial_size, int):
+        ph = pw = int(spatial_size)
+    else:
+        ph, pw = (int(v) for v in spatial_size)
+    if ph > H or pw > W or ph <= 0 or pw <= 0:
+        raise nat.SpclError(f"spatial_size {(ph, pw)} must pool down from {(H, W)}")
+    if points is not None:
+        if points.dim() != 2 or points.shape[0] != x.shape[0]:
+            raise ValueError(f"points must be [B, P], got {tuple(points.shape)} for B = {x.shape[0]}")
+        if not points.is_cuda:                       # host-made coordinates: range-check without a device sync
+            if points.numel() and (int(points.min()) < 0 or int(points.max()) >= ph * pw):
+                raise IndexError(f"point coordinate outside the {ph} x {pw} pooled grid")
+        points = points.to(device=x.device, dtype=torch.int32).contiguous()
+    y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps))
+    return y

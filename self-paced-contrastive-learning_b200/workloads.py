@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-__all__ = ["acdc_meta_labels", "clustered_embeddings", "make_views", "WORKLOADS", "make_workload"]
+__all__ = ["acdc_meta_labels", "clustered_embeddings", "make_views", "WORKLOADS", "make_workload", "acdc_encoder"]
 
 
 def acdc_meta_labels(n: int) -> dict:
@@ -81,3 +81,26 @@ def make_workload(name: str, *, seed: int = 0, sigma: float = 0.7):
     else:
         z1, z2 = make_views(labels, d, sigma=sigma, seed=seed)
     return z1, z2, labels
+
+
+def acdc_encoder(input_dim: int = 1, max_channel: int = 256, momentum: float = 0.1):
+    """Stand-in for the cfg5 backbone, ``UNet(input_dim=1, num_classes=4, max_channel=256)(x, until="Conv5")``
+    (``semi_seg/arch/unet.py:100-170``): five double 3x3 conv + BatchNorm + ReLU stages of widths
+    max_channel/16 * (1, 2, 4, 8, 16) with 2x2 max-pools between them.  Written from the architecture's
+    description for the benchmark harness only (the UNet itself is outside the hot path, DESIGN.md section 8);
+    plain torch / cuDNN layers, random init."""
+    from torch import nn
+
+    def stage(cin, cout):
+        return nn.Sequential(
+            nn.Conv2d(cin, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout, momentum=momentum), nn.ReLU(inplace=True),
+            nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout, momentum=momentum), nn.ReLU(inplace=True))
+
+    widths = [max_channel // 16 * m for m in (1, 2, 4, 8, 16)]
+    layers, cin = [], input_dim
+    for k, cout in enumerate(widths):
+        if k:
+            layers.append(nn.MaxPool2d(2, 2))
+        layers.append(stage(cin, cout))
+        cin = cout
+    return nn.Sequential(*layers)

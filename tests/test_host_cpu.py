@@ -183,3 +183,75 @@ def test_symmetric_tile_walk_covers_the_triangle_exactly_once(RB, bn, vg):
     assert set(seen) == want
     assert max(counts) - min(counts) <= 1
     assert h.spcl_debug_sym_walk(RB, CT, bn, vg, vg, None, 0) == -1        # vb out of range
+
+
+# ---- hook-side glue and dense front end (8 f4): host logic --------------------------------------
+def test_encode_labels_equals_sklearn_label_encoder():
+    from spcl_b200.hooks import encode_labels
+    cases = [["b", "a", "c", "a"], ["patient010", "patient002", "patient010", "patient100"], [3, 1, 2, 1, 3],
+             ["0", "1", "2"] * 4]
+    assert encode_labels(cases[0]) == [1, 0, 2, 0]
+    assert encode_labels(cases[1]) == [1, 0, 1, 2]
+    sk = pytest.importorskip("sklearn.preprocessing")
+    for v in cases:
+        assert encode_labels(v) == sk.LabelEncoder().fit(v).transform(v).tolist()      # helper.py:48-55
+
+
+def test_get_label_dispatch_follows_reference():
+    from spcl_b200.hooks import get_label
+    part = ["0", "1", "2", "0", "1", "2"]
+    group = ["patient003_00", "patient003_00", "patient003_01", "patient001_00", "patient001_01", "patient001_01"]
+    assert get_label("partition", "acdc", part, group) == [0, 1, 2, 0, 1, 2]
+    assert get_label("patient", "acdc", part, group) == [1, 1, 1, 0, 0, 0]
+    assert get_label("cycle", "acdc", part, group) == [0, 0, 1, 0, 1, 1]
+    assert get_label("self", "acdc", part, group) == list(range(6))
+    assert get_label("patient", "prostate", part, group) == [1, 1, 1, 0, 0, 0]
+    with pytest.raises(NotImplementedError):
+        get_label("cycle", "prostate", part, group)           # hooks/utils.py:23-31: no cycle labels there
+    with pytest.raises(NotImplementedError):
+        get_label("partition", "unknown", part, group)
+
+
+def test_device_meter_and_label_cache():
+    from spcl_b200.hooks import DeviceMeter, LabelCache
+    m = DeviceMeter()
+    assert m.summary() != m.summary()                          # nan when empty
+    for v in (torch.tensor(1.0), torch.tensor(2.0), 6.0):
+        m.add(v)
+    assert m.summary() == pytest.approx(3.0)
+    m.reset()
+    m.add(4.0)
+    assert m.summary() == 4.0
+    cache = LabelCache(capacity=2)
+    a = cache([0, 1, 2], "cpu")
+    assert a.dtype == torch.int32 and a.tolist() == [0, 1, 2]
+    assert cache([0, 1, 2], "cpu") is a                        # second call: no new upload
+    cache([1], "cpu"); cache([2], "cpu")
+    assert cache([0, 1, 2], "cpu") is not a                    # evicted (LRU, capacity 2)
+
+
+def test_self_paced_gamma_schedule_steps_like_the_hook_factory():
+    from spcl_b200.hooks import SelfPacedGammaSchedule
+    s = SelfPacedGammaSchedule(mode="soft", p=0.5, begin_value=5.0, end_value=60.0, max_epoch=4, correct_grad=True)
+    seen = [s.new_epoch() for _ in range(4)]
+    assert seen == pytest.approx([5.0 + 55.0 * (e / 4) ** 0.5 for e in range(4)])       # infonce.py:46-49, :134-136
+    assert s.criterion.age_param == pytest.approx(seen[-1])
+
+
+def test_dense_abi_validates_arguments_without_touching_the_gpu():
+    h = nat.lib()
+    null, fake = ctypes.c_void_p(0), ctypes.c_void_p(4096)
+    assert h.spcl_dense_rows_fwd(null, null, 2, 8, 16, 16, 4, 4, 16, 1e-12, fake, fake, null) == -1
+    assert h.spcl_dense_rows_fwd(fake, null, 2, 8, 16, 16, 0, 4, 16, 1e-12, fake, fake, null) == -1
+    assert h.spcl_dense_rows_fwd(fake, null, 2, 8, 16, 16, 32, 4, 128, 1e-12, fake, fake, null) == -2   # pools up
+    assert h.spcl_dense_rows_fwd(fake, fake, 2, 8, 16, 16, 4, 4, 0, 1e-12, fake, fake, null) == -1      # P = 0
+    assert h.spcl_dense_rows_bwd(null, null, 2, 8, 16, 16, 4, 4, 16, fake, null) == -1
+    assert h.spcl_dense_rows_bwd(fake, null, 2, 8, 16, 16, 4, 32, 128, fake, null) == -2
+
+
+def test_dense_rows_rejects_cpu_tensors_and_bad_points():
+    import spcl_b200
+    with pytest.raises(RuntimeError):
+        spcl_b200.ops.dense_rows(torch.randn(1, 4, 8, 8), (4, 4))                   # no CPU path
+    with pytest.raises(ValueError):
+        spcl_b200.ops.dense_rows(torch.randn(4, 8, 8), (4, 4))

@@ -156,3 +156,46 @@ def test_zero_positive_row_is_nan():
     with pytest.raises(RuntimeError):
         dense_supcon(torch.from_numpy(z).float(), torch.from_numpy(z[::-1].copy()).float(),
                      mask=torch.from_numpy(tri).float(), mode="none")
+
+
+# ---- dense front end: oracle and host-side point draw vs the reference-generated fixture --------
+DENSE = Golden("dense_points.npz")
+
+
+@pytest.mark.parametrize("name", DENSE.cases)
+def test_dense_oracle_matches_reference_rows(name):
+    from oracle.dense_frontend import dense_rows
+    ph, pw, P, seed = (int(v) for v in DENSE[f"{name}/geom"])
+    x = DENSE[f"{name}/x"]
+    rows = dense_rows(x, ph, pw, points=DENSE[f"{name}/points"])
+    np.testing.assert_allclose(rows, DENSE[f"{name}/rows"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(dense_rows(x, ph, pw), DENSE[f"{name}/all_rows"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", DENSE.cases)
+def test_point_coordinates_reproduce_the_reference_draw(name):
+    """bit-exact: same legacy numpy stream as ``with FixRandomSeed(seed): region_extractor(...)``."""
+    import spcl_b200
+    ph, pw, P, seed = (int(v) for v in DENSE[f"{name}/geom"])
+    B = DENSE[f"{name}/x"].shape[0]
+    pts = spcl_b200.point_coordinates(B, ph, pw, P, seed=seed)
+    assert pts.dtype == torch.int32 and tuple(pts.shape) == (B, P)
+    assert np.array_equal(pts.numpy(), DENSE[f"{name}/points"])
+    # the global-generator form (seed=None) draws from numpy.random like the reference does
+    np.random.seed(seed)
+    assert np.array_equal(spcl_b200.point_coordinates(B, ph, pw, P).numpy(), DENSE[f"{name}/points"])
+
+
+def test_dense_oracle_gradient_is_the_adjoint():
+    from oracle.dense_frontend import dense_rows, dense_rows_grad
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 4, 7, 9))
+    pts = np.array([[0, 5, 11], [3, 3, 8]])          # repeated point: gradients add
+    for points in (None, pts):
+        y0 = dense_rows(x, 3, 4, points)
+        gy = rng.standard_normal(y0.shape)
+        g = dense_rows_grad(x, 3, 4, gy, points)
+        dx = rng.standard_normal(x.shape)
+        h = 1e-6
+        fd = ((dense_rows(x + h * dx, 3, 4, points) - dense_rows(x - h * dx, 3, 4, points)) * gy).sum() / (2 * h)
+        assert np.isclose((g * dx).sum(), fd, rtol=1e-6, atol=1e-8)
