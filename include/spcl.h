@@ -182,6 +182,34 @@ int spcl_supcon_bwd_f32_split(const float* z, int64_t n_total, int32_t d, int64_
                               const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
                               int mode, float* dz, int64_t lddz, spcl_stream_t stream);
 
+/* ---- grouped launch: the K meta-label losses of one training step (partition / patient / cycle, each with its own
+ * projector output, labels and gamma: poster Eq. 4, semi_seg creator.py:102-124, run_self_paced_acdc:61-70) as ONE
+ * launch per stage instead of K x (5..6) launches.  Label form, whole problems (no row sharding), modes NONE / HARD /
+ * SOFT; every problem obeys the contract of spcl_supcon_fwd_f32_split / _bwd_f32_split and additionally gets its
+ * scalars[4] = { loss, downgrade_ratio, scale, scale / N } (what spcl_supcon_finalize writes).  The forward zeroes
+ * acc and partials itself; the backward fully writes dz [n_total][lddz].  `problems` is a HOST array, copied into
+ * the kernel arguments; count <= SPCL_MAX_GROUP (SPCL_ERR_UNSUPPORTED above). */
+#define SPCL_MAX_GROUP 8
+typedef struct spcl_problem_f32 {
+  const float* z;          /* [n_total][ldz] unit rows, view 1 then view 2 (contrast_loss3.py:26) */
+  int64_t n_total;
+  int32_t d;
+  int64_t ldz;
+  const int32_t* labels;   /* [n_total] */
+  float inv_tau, gamma;
+  int mode, correct_grad;
+  float* acc;              /* fwd scratch: float [n_total][4], 16-byte aligned */
+  float* row_stats;        /* fwd out / bwd in: 4 planes of stats_stride floats */
+  int64_t stats_stride;
+  float* partials;         /* fwd scratch/out: float[3] */
+  float* scalars;          /* fwd out / bwd in: float[4] */
+  const float* grad_out;   /* bwd in: d(total)/d(loss), float[1] on the device */
+  float* dz;               /* bwd out: [n_total][lddz] */
+  int64_t lddz;
+} spcl_problem_f32;
+int spcl_supcon_group_fwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream);
+int spcl_supcon_group_bwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream);
+
 /* ---- scalar epilogue (after the optional all-reduce of partials) ------------------------------
  * scalars = { loss, ratio, scale, scale / N }; scale = 1/ratio if correct_grad and ratio > 0
  * (contrast_loss3.py:189-201).  A NaN loss is reported by the host wrapper as RuntimeError (:203). */

@@ -51,7 +51,18 @@ SIGNATURES = {
     "spcl_supcon_bwd_f32_split": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _f32, _f32,
                                   _c.c_int, _ptr, _i64, _ptr],
     "spcl_supcon_finalize": [_ptr, _i64, _c.c_int, _ptr, _ptr],
+    "spcl_supcon_group_fwd_f32": [_ptr, _c.c_int, _ptr],
+    "spcl_supcon_group_bwd_f32": [_ptr, _c.c_int, _ptr],
 }
+MAX_GROUP = 8
+
+
+class ProblemF32(_c.Structure):
+    """``spcl_problem_f32`` of include/spcl.h (field order and types must match)."""
+    _fields_ = [("z", _ptr), ("n_total", _i64), ("d", _i32), ("ldz", _i64), ("labels", _ptr),
+                ("inv_tau", _f32), ("gamma", _f32), ("mode", _c.c_int), ("correct_grad", _c.c_int),
+                ("acc", _ptr), ("row_stats", _ptr), ("stats_stride", _i64), ("partials", _ptr), ("scalars", _ptr),
+                ("grad_out", _ptr), ("dz", _ptr), ("lddz", _i64)]
 OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error")
 ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS
 

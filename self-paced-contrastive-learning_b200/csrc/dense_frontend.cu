@@ -30,22 +30,37 @@ constexpr int kMaxW = 1024;    // per-warp column-sum staging (floats)
 // y[(b*ph + i)*pw + j][0..C).
 // dynamic shared memory: C * (pw + 1) floats (pooled) + 8 * W floats (column sums)
 // ------------------------------------------------------------------------------------------------
+template <bool VEC4>
 __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x, float* __restrict__ y,
                                                      float* __restrict__ inv_norm, int C, int H, int W, int ph,
                                                      int pw, float eps) {
   extern __shared__ float smem[];
   float* pooled = smem;                                  // [C][pw + 1]
-  float* colsum = smem + (size_t)C * (pw + 1);           // [8][W]
+  float* colsum = smem + (((size_t)C * (pw + 1) + 3) & ~(size_t)3);   // [8][W], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / ph, i = blockIdx.x % ph;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
   float* cs = colsum + (size_t)warp * W;
   for (int c = warp; c < C; c += 8) {
     const float* xc = x + ((int64_t)b * C + c) * H * W;
-    for (int w = lane; w < W; w += 32) {
-      float s = 0.f;
-      for (int h = hs; h < he; ++h) s += xc[(int64_t)h * W + w];
-      cs[w] = s;
+    if (VEC4) {                      // W % 4 == 0 and x 16-byte aligned: 16-byte loads, 4 columns per lane
+      const float4* x4 = reinterpret_cast<const float4*>(xc);
+      const int W4 = W >> 2;
+      for (int w4 = lane; w4 < W4; w4 += 32) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int h = hs; h < he; ++h) {
+          const float4 v = __ldg(x4 + (int64_t)h * W4 + w4);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        reinterpret_cast<float4*>(cs)[w4] = s;
+      }
+    } else {
+      for (int w = lane; w < W; w += 32) {
+        float s = 0.f;
+        for (int h = hs; h < he; ++h) s += xc[(int64_t)h * W + w];
+        cs[w] = s;
+      }
     }
     __syncwarp();
     for (int j = lane; j < pw; j += 32) {
@@ -69,27 +84,41 @@ __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x
 }
 
 // gx[b][c][h][w] = sum over the (<= 2 x 2) pooling windows containing (h, w) of gp[row(b,i,j)][c] / area(i,j)
-// gp = gradient with respect to the POOLED (un-normalised) values, rows layout.
-__global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, float* __restrict__ gx, int64_t B,
-                                                     int C, int H, int W, int ph, int pw) {
-  const int64_t total = B * C * H * W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(t % W);
-    const int h = (int)((t / W) % H);
-    const int c = (int)((t / ((int64_t)W * H)) % C);
-    const int64_t b = t / ((int64_t)W * H * C);
-    const int i0 = (int)(((int64_t)h * ph) / H), j0 = (int)(((int64_t)w * pw) / W);
-    float g = 0.f;
-    for (int i = max(i0 - 1, 0); i <= min(i0 + 1, ph - 1); ++i) {
-      const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
-      if (h < hs || h >= he) continue;
-      for (int j = max(j0 - 1, 0); j <= min(j0 + 1, pw - 1); ++j) {
-        const int ws = win_begin(j, W, pw), we = win_end(j, W, pw);
-        if (w < ws || w >= we) continue;
-        g += gp[((b * ph + i) * pw + j) * C + c] / (float)((he - hs) * (we - ws));
-      }
+// gp = gradient with respect to the POOLED (un-normalised) values, rows layout [b][i][j][c].
+// One CTA per (image b, input row h): the <= 2 pooled rows that contain h are read coalesced along c, scaled by
+// 1 / area and summed into G[c][j] in shared memory (the transpose), then every channel's input row is written
+// coalesced along w as G[c][j0(w)] (+ G[c][j0(w) + 1] when the next window also covers w).
+// dynamic shared memory: C * (pw + 1) floats
+__global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, float* __restrict__ gx, int C,
+                                                     int H, int W, int ph, int pw) {
+  extern __shared__ float G[];                            // [C][pw + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int i0 = (int)(((int64_t)h * ph) / H);
+  int irow[2], ilen[2], ni = 0;
+  for (int i = i0; i <= min(i0 + 1, ph - 1); ++i) {
+    const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
+    if (h >= hs && h < he) { irow[ni] = i; ilen[ni] = he - hs; ++ni; }
+  }
+  for (int j = warp; j < pw; j += 8) {
+    const int wlen = win_end(j, W, pw) - win_begin(j, W, pw);
+    for (int c = lane; c < C; c += 32) {
+      float g = 0.f;
+      for (int k = 0; k < ni; ++k)
+        g += __ldg(gp + (((int64_t)b * ph + irow[k]) * pw + j) * C + c) / (float)(ilen[k] * wlen);
+      G[c * (pw + 1) + j] = g;
     }
-    gx[t] = g;
+  }
+  __syncthreads();
+  for (int w = lane; w < W; w += 32) {
+    const int j0 = (int)(((int64_t)w * pw) / W);
+    const bool two = (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
+    float* out = gx + (((int64_t)b * C) * H + h) * W + w;
+    for (int c = warp; c < C; c += 8) {
+      float g = G[c * (pw + 1) + j0];
+      if (two) g += G[c * (pw + 1) + j0 + 1];
+      out[(int64_t)c * H * W] = g;
+    }
   }
 }
 
@@ -164,12 +193,13 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (points == nullptr) {
     if (W > dense::kMaxW) return SPCL_ERR_UNSUPPORTED;
-    const size_t smem = sizeof(float) * ((size_t)C * (pw + 1) + 8 * (size_t)W);
+    const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 8 * (size_t)W);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
+    const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    auto kern = vec4 ? dense::pool_rows_fwd<true> : dense::pool_rows_fwd<false>;
     if (smem > 48 * 1024)
-      SPCL_CUDA_TRY(cudaFuncSetAttribute(dense::pool_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense::pool_rows_fwd<<<(unsigned)(B * ph), 256, smem, s>>>(x, y, inv_norm, (int)C, (int)H, (int)W, (int)ph,
-                                                              (int)pw, eps);
+      SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(B * ph), 256, smem, s>>>(x, y, inv_norm, (int)C, (int)H, (int)W, (int)ph, (int)pw, eps);
   } else {
     if (P <= 0 || P > INT_MAX) return SPCL_ERR_INVALID_ARG;
     const int64_t rows = B * P;
@@ -187,9 +217,12 @@ extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points,
   if (ph > H || pw > W) return SPCL_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (points == nullptr) {
-    int64_t blocks = ceil_div(B * C * H * W, 256);
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
-    dense::pool_rows_bwd<<<(unsigned)blocks, 256, 0, s>>>(g_pooled, gx, B, (int)C, (int)H, (int)W, (int)ph, (int)pw);
+    if (B * H > INT_MAX) return SPCL_ERR_INVALID_ARG;
+    const size_t smem = sizeof(float) * (size_t)C * (pw + 1);
+    if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+      SPCL_CUDA_TRY(cudaFuncSetAttribute(dense::pool_rows_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense::pool_rows_bwd<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
   } else {
     if (P <= 0 || P > INT_MAX) return SPCL_ERR_INVALID_ARG;
     SPCL_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * B * C * H * W, s));

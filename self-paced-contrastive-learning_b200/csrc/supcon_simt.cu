@@ -356,7 +356,7 @@ __device__ __forceinline__ void split_rows(const Args& p, int64_t i0, int ty, in
 
 // PASS 0: rowsum, c, sum P <z_i, z_j>;  PASS 1: sum P W LLH, sum P W (needs the complete rowsum of PASS 0)
 template <int PASS>
-__global__ void __launch_bounds__(NT) fwd_split_kernel(Args p, Split sp, float4* __restrict__ acc) {
+__device__ __forceinline__ void fwd_split_body(const Args& p, const Split sp, float4* __restrict__ acc) {
   __shared__ Smem sm;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
@@ -418,11 +418,16 @@ __global__ void __launch_bounds__(NT) fwd_split_kernel(Args p, Split sp, float4*
   }
 }
 
+template <int PASS>
+__global__ void __launch_bounds__(NT) fwd_split_kernel(Args p, Split sp, float4* __restrict__ acc) {
+  fwd_split_body<PASS>(p, sp, acc);
+}
+
 // row_stats planes {logD, 1/c, A, u} and the three partial sums from the complete acc (cf. fwd_kernel's epilogue)
-__global__ void __launch_bounds__(256) row_finalize_split_kernel(const float4* __restrict__ acc, int64_t row_begin,
-                                                                 int64_t row_end, int64_t sld, float inv_tau,
-                                                                 int mode, float* __restrict__ row_stats,
-                                                                 float* __restrict__ partials) {
+__device__ __forceinline__ void row_finalize_split_body(const float4* __restrict__ acc, int64_t row_begin,
+                                                        int64_t row_end, int64_t sld, float inv_tau, int mode,
+                                                        float* __restrict__ row_stats,
+                                                        float* __restrict__ partials) {
   __shared__ float red[3][8];
   const int64_t gi = row_begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   float l = 0.f, w = 0.f, c = 0.f;
@@ -456,11 +461,18 @@ __global__ void __launch_bounds__(256) row_finalize_split_kernel(const float4* _
   }
 }
 
+__global__ void __launch_bounds__(256) row_finalize_split_kernel(const float4* __restrict__ acc, int64_t row_begin,
+                                                                 int64_t row_end, int64_t sld, float inv_tau,
+                                                                 int mode, float* __restrict__ row_stats,
+                                                                 float* __restrict__ partials) {
+  row_finalize_split_body(acc, row_begin, row_end, sld, inv_tau, mode, row_stats, partials);
+}
+
 template <int DV>
-__global__ void __launch_bounds__(NT) bwd_split_kernel(Args p, Split sp, const float* __restrict__ row_stats,
-                                                       int64_t sld, const float* __restrict__ scalars,
-                                                       const float* __restrict__ grad_out, float* __restrict__ dz,
-                                                       int64_t lddz) {
+__device__ __forceinline__ void bwd_split_body(const Args& p, const Split sp, const float* __restrict__ row_stats,
+                                               int64_t sld, const float* __restrict__ scalars,
+                                               const float* __restrict__ grad_out, float* __restrict__ dz,
+                                               int64_t lddz, const bool single) {
   __shared__ Smem sm;
   __shared__ float ts[BM][BN + 1];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -526,7 +538,6 @@ __global__ void __launch_bounds__(NT) bwd_split_kernel(Args p, Split sp, const f
   }
 
   const float coef = grad_out[0] * scalars[3] * p.inv_tau;
-  const bool single = gridDim.y == 1;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     if (gi[a] >= p.row_end) continue;
@@ -541,6 +552,81 @@ __global__ void __launch_bounds__(NT) bwd_split_kernel(Args p, Split sp, const f
   }
 }
 
+template <int DV>
+__global__ void __launch_bounds__(NT) bwd_split_kernel(Args p, Split sp, const float* __restrict__ row_stats,
+                                                       int64_t sld, const float* __restrict__ scalars,
+                                                       const float* __restrict__ grad_out, float* __restrict__ dz,
+                                                       int64_t lddz) {
+  bwd_split_body<DV>(p, sp, row_stats, sld, scalars, grad_out, dz, lddz, gridDim.y == 1);
+}
+
+// ---- grouped launches: K <= SPCL_MAX_GROUP independent problems (the K meta-label losses of one training step,
+// poster Eq. 4 / semi_seg creator.py:102-124) share every launch; blockIdx.z selects the problem.
+struct Group {
+  Args p[SPCL_MAX_GROUP];
+  Split sp[SPCL_MAX_GROUP];
+  unsigned gx[SPCL_MAX_GROUP], gy[SPCL_MAX_GROUP];
+  float4* acc[SPCL_MAX_GROUP];
+  float* row_stats[SPCL_MAX_GROUP];
+  int64_t sld[SPCL_MAX_GROUP];
+  float* partials[SPCL_MAX_GROUP];
+  float* scalars[SPCL_MAX_GROUP];
+  int correct_grad[SPCL_MAX_GROUP];
+  const float* grad_out[SPCL_MAX_GROUP];
+  float* dz[SPCL_MAX_GROUP];
+  int64_t lddz[SPCL_MAX_GROUP];
+};
+
+// zeroes acc + partials (forward) or dz (backward) of every problem: one launch instead of K memsets
+template <bool BWD>
+__global__ void __launch_bounds__(256) group_zero_kernel(const __grid_constant__ Group g) {
+  const int k = blockIdx.z;
+  const Args& p = g.p[k];
+  if (BWD) {
+    const int64_t total = p.N * g.lddz[k];
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      g.dz[k][t] = 0.f;
+  } else {
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < p.N;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      g.acc[k][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blockIdx.x == 0 && threadIdx.x < 3) g.partials[k][threadIdx.x] = 0.f;
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(NT) fwd_split_group_kernel(const __grid_constant__ Group g) {
+  const int k = blockIdx.z;
+  if (blockIdx.x >= g.gx[k] || blockIdx.y >= g.gy[k]) return;
+  if (PASS == 1 && g.p[k].mode == SPCL_MODE_NONE) return;
+  fwd_split_body<PASS>(g.p[k], g.sp[k], g.acc[k]);
+}
+
+__global__ void __launch_bounds__(256) row_finalize_group_kernel(const __grid_constant__ Group g) {
+  const int k = blockIdx.z;
+  const Args& p = g.p[k];
+  if (static_cast<int64_t>(blockIdx.x) * blockDim.x >= p.N) return;
+  row_finalize_split_body(g.acc[k], 0, p.N, g.sld[k], p.inv_tau, p.mode, g.row_stats[k], g.partials[k]);
+}
+
+__device__ __forceinline__ void finalize_body(const float* __restrict__ partials, float n_total, int correct_grad,
+                                              float* __restrict__ scalars);
+
+__global__ void finalize_group_kernel(const __grid_constant__ Group g) {
+  const int k = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  finalize_body(g.partials[k], static_cast<float>(g.p[k].N), g.correct_grad[k], g.scalars[k]);
+}
+
+template <int DV>
+__global__ void __launch_bounds__(NT) bwd_split_group_kernel(const __grid_constant__ Group g) {
+  const int k = blockIdx.z;
+  if (blockIdx.x >= g.gx[k] || blockIdx.y >= g.gy[k]) return;
+  bwd_split_body<DV>(g.p[k], g.sp[k], g.row_stats[k], g.sld[k], g.scalars[k], g.grad_out[k], g.dz[k], g.lddz[k],
+                     false);
+}
+
 // column tiles per CTA so that the grid has about two CTAs per SM
 static Split pick_split(int64_t rows, int64_t n_total, unsigned& gy) {
   const int64_t rb = ceil_div(rows, static_cast<int64_t>(BM)), ct = ceil_div(n_total, static_cast<int64_t>(BN));
@@ -551,9 +637,8 @@ static Split pick_split(int64_t rows, int64_t n_total, unsigned& gy) {
   return Split{static_cast<int>(per)};
 }
 
-__global__ void finalize_kernel(const float* __restrict__ partials, float n_total, int correct_grad,
-                                float* __restrict__ scalars) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void finalize_body(const float* __restrict__ partials, float n_total, int correct_grad,
+                                              float* __restrict__ scalars) {
   const float loss_sum = partials[0], wp = partials[1], pc = partials[2];
   const float ratio = wp / pc;                       // 0/0 -> NaN, like mean() of an empty selection (:189)
   const float scale = (correct_grad && ratio > 0.f) ? 1.f / ratio : 1.f;   // :199-201
@@ -561,6 +646,12 @@ __global__ void finalize_kernel(const float* __restrict__ partials, float n_tota
   scalars[1] = ratio;
   scalars[2] = scale;
   scalars[3] = scale / n_total;
+}
+
+__global__ void finalize_kernel(const float* __restrict__ partials, float n_total, int correct_grad,
+                                float* __restrict__ scalars) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  finalize_body(partials, n_total, correct_grad, scalars);
 }
 
 static int check_common(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
@@ -679,5 +770,80 @@ extern "C" int spcl_supcon_bwd_f32_split(const float* z, int64_t n_total, int32_
   else if (d <= 128) simt::bwd_split_kernel<8><<<grid, simt::NT, 0, s>>>(a, sp, row_stats, stats_stride, scalars, grad_out, dz, lddz);
   else simt::bwd_split_kernel<16><<<grid, simt::NT, 0, s>>>(a, sp, row_stats, stats_stride, scalars, grad_out, dz, lddz);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_f32_split");
+  return SPCL_OK;
+}
+
+// ---- grouped label-form problems (whole problems, no row sharding): one launch per stage for all K --------------
+static int fill_group(const spcl_problem_f32* pr, int count, bool bwd, simt::Group& g, unsigned& gx, unsigned& gy,
+                      int& dmax, bool& any_sp, int64_t& nmax) {
+  if (pr == nullptr || count <= 0) return SPCL_ERR_INVALID_ARG;
+  if (count > SPCL_MAX_GROUP) return SPCL_ERR_UNSUPPORTED;
+  gx = gy = 1; dmax = 0; any_sp = false; nmax = 0;
+  for (int k = 0; k < count; ++k) {
+    const spcl_problem_f32& q = pr[k];
+    int rc = simt::check_common(q.z, q.n_total, q.d, q.ldz, q.labels, nullptr, 0, 0, q.n_total, q.inv_tau, q.gamma,
+                                q.mode);
+    if (rc != SPCL_OK) return rc;
+    if (q.mode == SPCL_MODE_EXCL) return SPCL_ERR_UNSUPPORTED;
+    if (q.row_stats == nullptr || q.scalars == nullptr || q.stats_stride < q.n_total) return SPCL_ERR_INVALID_ARG;
+    if (!bwd && (q.acc == nullptr || q.partials == nullptr || (reinterpret_cast<uintptr_t>(q.acc) & 15)))
+      return SPCL_ERR_INVALID_ARG;
+    if (bwd && (q.grad_out == nullptr || q.dz == nullptr || q.lddz < q.d)) return SPCL_ERR_INVALID_ARG;
+    g.p[k] = simt::Args{q.z, q.n_total, q.d, q.ldz, q.labels, nullptr, 0, 0, q.n_total, q.inv_tau, q.gamma,
+                        1.f / q.gamma, q.mode};
+    g.sp[k] = simt::pick_split(q.n_total, q.n_total, g.gy[k]);
+    g.gx[k] = static_cast<unsigned>(ceil_div(q.n_total, static_cast<int64_t>(simt::BM)));
+    g.acc[k] = reinterpret_cast<float4*>(q.acc);
+    g.row_stats[k] = q.row_stats;
+    g.sld[k] = q.stats_stride;
+    g.partials[k] = q.partials;
+    g.scalars[k] = q.scalars;
+    g.correct_grad[k] = q.correct_grad;
+    g.grad_out[k] = q.grad_out;
+    g.dz[k] = q.dz;
+    g.lddz[k] = q.lddz;
+    if (g.gx[k] > gx) gx = g.gx[k];
+    if (g.gy[k] > gy) gy = g.gy[k];
+    if (q.d > dmax) dmax = q.d;
+    if (q.n_total > nmax) nmax = q.n_total;
+    any_sp = any_sp || q.mode != SPCL_MODE_NONE;
+  }
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_group_fwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream) {
+  simt::Group g{};
+  unsigned gx, gy; int dmax; bool any_sp; int64_t nmax;
+  int rc = fill_group(problems, count, false, g, gx, gy, dmax, any_sp, nmax);
+  if (rc != SPCL_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned K = static_cast<unsigned>(count);
+  const unsigned zb = static_cast<unsigned>(ceil_div(nmax, static_cast<int64_t>(256)));
+  simt::group_zero_kernel<false><<<dim3(zb, 1, K), 256, 0, s>>>(g);
+  simt::fwd_split_group_kernel<0><<<dim3(gx, gy, K), simt::NT, 0, s>>>(g);
+  if (any_sp) simt::fwd_split_group_kernel<1><<<dim3(gx, gy, K), simt::NT, 0, s>>>(g);
+  simt::row_finalize_group_kernel<<<dim3(zb, 1, K), 256, 0, s>>>(g);
+  simt::finalize_group_kernel<<<K, 32, 0, s>>>(g);
+  SPCL_LAUNCH_CHECK("spcl_supcon_group_fwd_f32");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_group_bwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream) {
+  simt::Group g{};
+  unsigned gx, gy; int dmax; bool any_sp; int64_t nmax;
+  int rc = fill_group(problems, count, true, g, gx, gy, dmax, any_sp, nmax);
+  if (rc != SPCL_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned K = static_cast<unsigned>(count);
+  int64_t zmax = 0;
+  for (int k = 0; k < count; ++k) zmax = zmax > problems[k].n_total * problems[k].lddz ? zmax : problems[k].n_total * problems[k].lddz;
+  unsigned zb = static_cast<unsigned>(ceil_div(zmax, static_cast<int64_t>(256 * 4)));
+  if (zb > 148 * 4) zb = 148 * 4;
+  simt::group_zero_kernel<true><<<dim3(zb, 1, K), 256, 0, s>>>(g);
+  const dim3 grid(gx, gy, K);
+  if (dmax <= 64) simt::bwd_split_group_kernel<4><<<grid, simt::NT, 0, s>>>(g);
+  else if (dmax <= 128) simt::bwd_split_group_kernel<8><<<grid, simt::NT, 0, s>>>(g);
+  else simt::bwd_split_group_kernel<16><<<grid, simt::NT, 0, s>>>(g);
+  SPCL_LAUNCH_CHECK("spcl_supcon_group_bwd_f32");
   return SPCL_OK;
 }

@@ -32,7 +32,7 @@ from torch import Tensor, nn
 from . import _native as nat
 from . import ops
 
-__all__ = ["SupConLoss1", "SelfPacedSupConLoss", "supcon_loss", "is_normalized"]
+__all__ = ["SupConLoss1", "SelfPacedSupConLoss", "supcon_loss", "is_normalized", "grouped_forward"]
 
 _AUTO_TC_MIN_N = 1024
 _DIAG_MAX_N = 16384
@@ -277,3 +277,41 @@ class SelfPacedSupConLoss(_FusedSupConBase):
         return self._ratio_cache
 
     sp_mask = property(lambda self: self._diag_get("sp_mask"))
+
+
+def grouped_forward(criteria, feats, targets=None):
+    """The K contrastive losses of one training step -- one criterion, projector output pair and label list per
+    meta-label (partition / patient / cycle; poster Eq. 4, ``semi_seg`` ``creator.py:102-124``) -- evaluated with ONE
+    kernel launch per stage for the whole group instead of K separate forward calls.  Equivalent to
+    ``[c(z1, z2, target=t) for c, (z1, z2), t in zip(criteria, feats, targets)]`` (same losses, gradients,
+    ``downgrade_ratio``); problems the grouped fp32 kernels do not carry (tensor-core sizes, ``exclude_other_pos``)
+    make the whole group run as those separate calls.  The N x N diagnostics are not kept for grouped calls."""
+    K = len(criteria)
+    targets = [None] * K if targets is None else list(targets)
+    if len(feats) != K or len(targets) != K:
+        raise ValueError("criteria, feats and targets must have the same length")
+    metas, labels, groupable = [], [], K <= nat.MAX_GROUP
+    for crit, (z1, z2), t in zip(criteria, feats, targets):
+        assert z1.shape == z2.shape, (z1.shape, z2.shape)
+        if crit._validate:
+            assert is_normalized(z1) and is_normalized(z2), "features need to be normalized first"
+        gamma, mode, cg = crit._gamma_mode_cg()
+        n = z1.shape[0]
+        if int(mode) == nat.MODE_EXCL or _pick_tc(crit._precision, 2 * n, False, int(mode)):
+            groupable = False
+        metas.append((crit._t, gamma, mode, cg))
+    if not groupable:
+        return [c(z1, z2, target=t) for c, (z1, z2), t in zip(criteria, feats, targets)]
+    for (z1, _), t in zip(feats, targets):
+        n, dev = z1.shape[0], z1.device
+        lab = ops.label_codes(t, n, dev) if t is not None else torch.arange(n, dtype=torch.int32, device=dev)
+        labels.append(lab.repeat(2))
+    scalars = ops.supcon_group_f32(list(feats), labels, metas)
+    out = []
+    for crit, sc in zip(criteria, scalars):
+        crit._scalars, crit._ratio_cache, crit._diag = sc.detach(), None, None
+        loss = sc[0]
+        if crit._check_nan and torch.isnan(loss):
+            raise RuntimeError(loss)
+        out.append(loss)
+    return out

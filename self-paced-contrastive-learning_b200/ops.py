@@ -532,3 +532,77 @@ def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: fl
         points = points.to(device=x.device, dtype=torch.int32).contiguous()
     y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps))
     return y
+
+
+# --------------------------------------------------------------------------------------------------
+# grouped launch: the K meta-label losses of one step share every kernel launch
+# --------------------------------------------------------------------------------------------------
+class _GroupSupCon(torch.autograd.Function):
+    """fp32 label-form problems; inputs z1_0, z2_0, z1_1, z2_1, ...; outputs one scalars[4] per problem."""
+
+    @staticmethod
+    def forward(ctx, meta, labels, *views):
+        K = len(meta)
+        dev = views[0].device
+        st = _stream(views[0])
+        shapes = [tuple(views[2 * k].shape) for k in range(K)]
+        # one workspace for every problem's acc [N,4] | row_stats [4,N] | partials [4] | scalars [4]
+        offs, total = [], 0
+        for n, d in shapes:
+            offs.append(total)
+            total += 2 * n * 8 + 8
+        ws = torch.empty(total, dtype=torch.float32, device=dev)
+        probs = (nat.ProblemF32 * K)()
+        zs, scal = [], []
+        for k, ((n, d), (temperature, gamma, mode, cg)) in enumerate(zip(shapes, meta)):
+            N = 2 * n
+            z = torch.cat([views[2 * k], views[2 * k + 1]], dim=0)          # contrast_loss3.py:26
+            zs.append(z)
+            base = ws[offs[k]:]
+            acc, stats = base[:N * 4], base[N * 4:N * 8]
+            partials, scalars = base[N * 8:N * 8 + 4], base[N * 8 + 4:N * 8 + 8]
+            scal.append(scalars)
+            q = probs[k]
+            q.z, q.n_total, q.d, q.ldz, q.labels = z.data_ptr(), N, d, z.stride(0), labels[k].data_ptr()
+            q.inv_tau, q.gamma, q.mode, q.correct_grad = 1.0 / float(temperature), float(gamma), int(mode), int(bool(cg))
+            q.acc, q.row_stats, q.stats_stride = acc.data_ptr(), stats.data_ptr(), N
+            q.partials, q.scalars = partials.data_ptr(), scalars.data_ptr()
+        nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(probs), K, st)
+        ctx.probs, ctx.keep, ctx.shapes = probs, (ws, zs, labels), shapes
+        return tuple(scal)
+
+    @staticmethod
+    def backward(ctx, *g_scalars):
+        probs, shapes = ctx.probs, ctx.shapes
+        K = len(shapes)
+        ws, zs, labels = ctx.keep
+        st = _stream(ws)
+        grads, hold = [], []
+        for k, (n, d) in enumerate(shapes):
+            g = g_scalars[k]
+            g0 = (torch.zeros(1, dtype=torch.float32, device=ws.device) if g is None else g.float().contiguous()[0:1])
+            dz = torch.empty(2 * n, d, dtype=torch.float32, device=ws.device)
+            hold.append(g0)
+            probs[k].grad_out, probs[k].dz, probs[k].lddz = g0.data_ptr(), dz.data_ptr(), d
+            grads += [dz[:n], dz[n:]]
+        nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(probs), K, st)
+        return (None, None, *grads)
+
+
+def supcon_group_f32(views, labels, meta):
+    """``views``: [(z1, z2), ...] fp32 unit rows; ``labels``: per problem int32 [2n] (both views, already tiled);
+    ``meta``: per problem (temperature, gamma, mode, correct_grad).  -> list of scalars[4] tensors."""
+    K = len(views)
+    if not 1 <= K <= nat.MAX_GROUP:
+        raise nat.SpclError(f"a group holds 1..{nat.MAX_GROUP} problems, got {K}")
+    flat = []
+    for (z1, z2), lab in zip(views, labels):
+        _require_cuda(z1, z2, lab)
+        if z1.shape != z2.shape or z1.dim() != 2:
+            raise AssertionError((tuple(z1.shape), tuple(z2.shape)))
+        if z1.shape[1] > nat.MAX_D:
+            raise nat.SpclError(f"embedding width {z1.shape[1]} > {nat.MAX_D} is not supported by this build")
+        if lab.dtype != torch.int32 or lab.shape != (2 * z1.shape[0],):
+            raise TypeError("labels must be int32[2n]")
+        flat += [z1.float().contiguous(), z2.float().contiguous()]
+    return list(_GroupSupCon.apply(tuple(meta), tuple(labels), *flat))

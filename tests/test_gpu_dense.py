@@ -213,3 +213,50 @@ def test_cfg5_encoder_step_fused_vs_reference_loss():
         # identical weights and inputs: the two arms may only drift by fp32 rounding through the optimiser
         assert vals["fused"][0] == pytest.approx(vals["ref"][0], rel=1e-3), (step, vals)
         assert vals["fused"][1] == pytest.approx(vals["ref"][1], rel=2e-2), (step, vals)
+
+
+# ---- grouped launch: K problems per launch == K separate calls -----------------------------
+@pytest.mark.parametrize("shapes", [
+    [(256, 256, "partition"), (256, 256, "patient"), (256, 256, "cycle")],            # cfg2
+    [(24, 64, "patient"), (100, 128, "composite"), (256, 256, "cycle"), (7, 16, "self")],   # ragged group
+    [(64, 128, "partition")],
+])
+def test_grouped_launch_equals_separate_calls(shapes):
+    from spcl_b200.workloads import make_views
+    specs = [("soft", 5.0, True), ("hard", 3.5, False), ("soft", 2.0, False), ("none", 1e6, False)]
+    crits_a, crits_b, feats_a, feats_b, targets = [], [], [], [], []
+    for k, (n, d, kind) in enumerate(shapes):
+        lab = acdc_meta_labels(n)[kind]
+        z1, z2 = make_views(lab, d, sigma=0.7, seed=k)
+        mode, gamma, cg = specs[k % len(specs)]
+        for crits, feats in ((crits_a, feats_a), (crits_b, feats_b)):
+            if mode == "none":
+                c = spcl_b200.SupConLoss1(precision="fp32")
+            else:
+                c = spcl_b200.SelfPacedSupConLoss(weight_update=mode, correct_grad=cg, precision="fp32")
+                c.set_gamma(gamma)
+            crits.append(c)
+            feats.append((z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True)))
+        targets.append(lab.tolist() if k % 2 else lab.int().cuda())
+    weights = [1.0, 0.5, 0.25, 2.0][:len(shapes)]
+    grouped = spcl_b200.grouped_forward(crits_a, feats_a, targets)
+    sum(w * l for w, l in zip(weights, grouped)).backward()
+    single = [c(z1, z2, target=t) for c, (z1, z2), t in zip(crits_b, feats_b, targets)]
+    sum(w * l for w, l in zip(weights, single)).backward()
+    for k in range(len(shapes)):
+        assert grouped[k].item() == pytest.approx(single[k].item(), rel=1e-5), k
+        if hasattr(crits_a[k], "downgrade_ratio"):
+            assert crits_a[k].downgrade_ratio == pytest.approx(crits_b[k].downgrade_ratio, rel=1e-5)
+        for ga, gb in zip(feats_a[k], feats_b[k]):
+            scale = gb.grad.abs().max().item()
+            assert (ga.grad - gb.grad).abs().max().item() <= 2e-5 * scale + 1e-12, k
+
+
+def test_grouped_launch_falls_back_to_separate_calls_for_tensor_core_sizes():
+    from spcl_b200.workloads import make_views
+    lab = torch.arange(1024) // 8
+    z1, z2 = make_views(lab, 128, sigma=0.7, seed=0)
+    c1, c2 = spcl_b200.SupConLoss1(), spcl_b200.SupConLoss1()
+    a = spcl_b200.grouped_forward([c1], [(z1.cuda(), z2.cuda())], [lab.tolist()])[0]          # N = 2048: bf16 path
+    b = c2(z1.cuda(), z2.cuda(), target=lab.tolist())
+    assert a.item() == pytest.approx(b.item(), rel=1e-6)

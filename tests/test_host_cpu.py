@@ -255,3 +255,32 @@ def test_dense_rows_rejects_cpu_tensors_and_bad_points():
         spcl_b200.ops.dense_rows(torch.randn(1, 4, 8, 8), (4, 4))                   # no CPU path
     with pytest.raises(ValueError):
         spcl_b200.ops.dense_rows(torch.randn(4, 8, 8), (4, 4))
+
+
+def test_problem_struct_matches_the_header(tmp_path):
+    """ctypes mirror of spcl_problem_f32 == the C compiler's layout of include/spcl.h."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "sz.c"
+    fields = [f[0] for f in nat.ProblemF32._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(spcl_problem_f32, {f}));' for f in fields)
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{ROOT}/include/spcl.h"\n'
+                   f'int main(void){{printf("%zu\\n", sizeof(spcl_problem_f32));{body}return 0;}}\n')
+    exe = tmp_path / "sz"
+    subprocess.run([cc, str(src), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(nat.ProblemF32)
+    assert out[1:] == [getattr(nat.ProblemF32, f).offset for f in fields]
+
+
+def test_group_abi_validates_arguments_without_touching_the_gpu():
+    h = nat.lib()
+    assert h.spcl_supcon_group_fwd_f32(None, 3, None) == -1
+    assert h.spcl_supcon_group_fwd_f32(ctypes.byref((nat.ProblemF32 * 9)()), 9, None) == -2       # > SPCL_MAX_GROUP
+    assert h.spcl_supcon_group_bwd_f32(ctypes.byref((nat.ProblemF32 * 2)()), 2, None) == -1       # null operands
+    import spcl_b200
+    with pytest.raises(ValueError):
+        spcl_b200.grouped_forward([spcl_b200.SupConLoss1()], [], None)

@@ -1,0 +1,46 @@
+"""HBM roofline of the dense front-end kernels (device-timed, L2 flushed between runs).
+    python tools/gpu_dense_bench.py > gpurun_out/dense_bench.json"""
+import json
+import pathlib
+import sys
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import spcl_b200                                            # noqa: E402
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6534.8
+
+
+def timed(fn, reps=10):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        fn()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+out = []
+for (B, C, H, W, ph, pw, P) in [(32, 128, 224, 224, 32, 32, None), (32, 128, 64, 64, 32, 32, None),
+                                (32, 128, 32, 32, 32, 32, None), (128, 128, 56, 56, 10, 10, 5)]:
+    x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    pts = None if P is None else spcl_b200.point_coordinates(B, ph, pw, P, seed=0).cuda()
+    rows = spcl_b200.ops.dense_rows(x, (ph, pw), pts)
+    gy = torch.randn_like(rows)
+    f_ms = timed(lambda: spcl_b200.ops.dense_rows(x.detach(), (ph, pw), pts))
+    b_ms = timed(lambda: torch.autograd.grad(rows, x, gy, retain_graph=True))
+    n_rows = rows.shape[0]
+    fwd_bytes = 4 * (B * C * H * W if P is None else n_rows * C * (H // ph + 1) * (W // pw + 1)) + 4 * n_rows * C
+    bwd_bytes = 4 * B * C * H * W + 3 * 4 * n_rows * C
+    out.append(dict(shape=[B, C, H, W], pooled=[ph, pw], points=P, fwd_ms=f_ms, bwd_ms=b_ms,
+                    fwd_gbs=fwd_bytes / f_ms / 1e6, bwd_gbs=bwd_bytes / b_ms / 1e6,
+                    fwd_frac=fwd_bytes / f_ms / 1e6 / PEAK, bwd_frac=bwd_bytes / b_ms / 1e6 / PEAK))
+print(json.dumps(dict(peak_gbs=PEAK, cases=out)))
