@@ -128,6 +128,25 @@ def run_reference(args, workload, world, rank):
     print(json.dumps(line), flush=True)
 
 
+def _ncu_traffic(which):
+    """dram bytes of the dominant kernel from the newest committed `ncu --set full` summary (profiles/*_ncu_<which>.txt,
+    same bench command, cfg3); a profiler figure cannot be taken inside this run.  -> (bytes | None, source)."""
+    import pathlib
+    import re
+    files = sorted((pathlib.Path(__file__).resolve().parent / "profiles").glob(f"r*_ncu_{which}.txt"))
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in reversed(files):
+        tot, seen = 0.0, 0
+        for line in f.read_text().splitlines():
+            m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.,]+)\s+(\w+)", line)
+            if m and m.group(3) in unit:
+                tot += float(m.group(2).replace(",", "")) * unit[m.group(3)]
+                seen += 1
+        if seen >= 2:
+            return tot, f"profiles/{f.name}"
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -248,6 +267,8 @@ def main():
         bwd_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
         fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(args.steps)]
+        for _ in range(3):                      # the custom-op dispatcher's first call carries one-time set-up
+            ops.supcon_fwd(a.detach(), b.detach(), lab, None, TAU, GAMMA, mode, False, True)
         for s, e in fev:
             flush.zero_()
             s.record()
@@ -256,9 +277,12 @@ def main():
         torch.cuda.synchronize()
         fwd_ms = sum(s.elapsed_time(e) for s, e in fev) / args.steps
         bwd_flops = 4.0 * rows * N * d
+        traffic, traffic_src = _ncu_traffic("bwd")
         roofline = {"bound": "tensor", "kernel": "spcl::tc::bwd_kernel (+dZ memset)",
                     "achieved": bwd_flops / (bwd_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "frac": bwd_flops / (bwd_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                    "frac": bwd_flops / (bwd_ms * 1e-3) / 1e12 / peak, "traffic": traffic,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "traffic_source": traffic_src,
                     "peak_source": f"{peak_src} burst (MEASURED_PEAKS.json bf16_tflops)",
                     "algorithmic_flops": bwd_flops, "kernel_ms": bwd_ms, "fwd_op_ms": fwd_ms,
                     "step_tflops_6N2d": 6.0 * rows * N * d / (ms_per_step * 1e-3) / 1e12,
