@@ -11,8 +11,10 @@
 // the sparse form never forms the pooled map.  Both kernels are streaming / HBM-bound; algorithmic bytes:
 //   all pooled pixels: 4*B*C*H*W read + 4*B*ph*pw*C write;   points: 4*B*P*C*window read + 4*B*P*C write.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace spcl {
 namespace dense {
@@ -48,17 +50,31 @@ __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x
       const int W4 = W >> 2;
       for (int w4 = lane; w4 < W4; w4 += 32) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int h = hs; h < he; ++h) {
-          const float4 v = __ldg(x4 + (int64_t)h * W4 + w4);
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        // predicated batches of 8 rows: every load of a batch is in flight before the first add (a runtime-trip
+        // unroll leaves a serial remainder loop: 4 DRAM round trips for a 7-row window instead of 1)
+        for (int h0 = hs; h0 < he; h0 += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)       // unconditional loads (row index clamped): ptxas batches them
+            v[k] = __ldg(x4 + (int64_t)min(h0 + k, he - 1) * W4 + w4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float m = (h0 + k < he) ? 1.f : 0.f;
+            s.x = fmaf(m, v[k].x, s.x); s.y = fmaf(m, v[k].y, s.y); s.z = fmaf(m, v[k].z, s.z); s.w = fmaf(m, v[k].w, s.w);
+          }
         }
         reinterpret_cast<float4*>(cs)[w4] = s;
       }
     } else {
       for (int w = lane; w < W; w += 32) {
         float s = 0.f;
-        for (int h = hs; h < he; ++h) s += xc[(int64_t)h * W + w];
+        for (int h0 = hs; h0 < he; h0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(xc + (int64_t)min(h0 + k, he - 1) * W + w);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s = fmaf((h0 + k < he) ? 1.f : 0.f, v[k], s);
+        }
         cs[w] = s;
       }
     }
@@ -70,6 +86,75 @@ __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x
       pooled[c * (pw + 1) + j] = s / (float)((he - hs) * (we - ws));
     }
     __syncwarp();
+  }
+  __syncthreads();
+  for (int j = warp; j < pw; j += 8) {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = pooled[c * (pw + 1) + j]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    const int64_t row = ((int64_t)b * ph + i) * pw + j;
+    if (lane == 0) inv_norm[row] = inv;
+    for (int c = lane; c < C; c += 32) y[row * C + c] = pooled[c * (pw + 1) + j] * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant of pool_rows_fwd (W % 4 == 0, windows of >= 1 KB): the window of one channel -- (he - hs) full
+// rows -- is ONE contiguous block of x, so each warp streams its channels through a private 2-stage shared-memory
+// ring with cp.async.bulk (1-D TMA) + mbarrier complete_tx: lane 0 issues channel k + 2 as soon as the warp has
+// finished reading channel k.  No registers are tied up by loads in flight (ptxas kept only ~2 of the LDG version's
+// 8 loads outstanding), 8 warps x 2 stages x ~6 KB = ~100 KB in flight per SM.
+// dynamic shared memory: pooled [C][pw + 1] | 16 mbarriers | stage [8 warps][2][stage_floats]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_rows_fwd_tma(const float* __restrict__ x, float* __restrict__ y,
+                                                         float* __restrict__ inv_norm, int C, int H, int W, int ph,
+                                                         int pw, float eps, int stage_floats) {
+  extern __shared__ __align__(128) float smem[];
+  float* pooled = smem;                                                        // [C][pw + 1]
+  const size_t pooled_floats = (((size_t)C * (pw + 1) + 31) & ~(size_t)31);    // 128-byte multiple
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pooled_floats);          // [8][2]
+  float* stages = smem + pooled_floats + 32;                                   // 16 barriers = 128 bytes
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / ph, i = blockIdx.x % ph;
+  const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
+  const int rows = he - hs;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 16; ++k) ptx::mbar_init(bars + k, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint64_t* bar = bars + warp * 2;
+  float* stage = stages + (size_t)warp * 2 * stage_floats;
+  const uint32_t bytes = (uint32_t)rows * (uint32_t)W * 4u;
+  const int nk = (C - warp + 7) / 8;                        // channels warp, warp + 8, ...
+  const float* src0 = x + (((int64_t)b * C + warp) * H + hs) * W;
+  const int64_t cstride = (int64_t)8 * H * W;
+  auto issue = [&](int k) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar + (k & 1), bytes);
+      ptx::bulk_load_1d(stage + (size_t)(k & 1) * stage_floats, src0 + k * cstride, bytes, bar + (k & 1));
+    }
+  };
+  if (nk > 0) issue(0);
+  if (nk > 1) issue(1);
+  for (int k = 0; k < nk; ++k) {
+    const int c = warp + 8 * k;
+    const float* st = stage + (size_t)(k & 1) * stage_floats;
+    ptx::mbar_wait(bar + (k & 1), (uint32_t)(k >> 1) & 1u);
+    for (int j = lane; j < pw; j += 32) {
+      const int ws = win_begin(j, W, pw), we = win_end(j, W, pw);
+      float s0 = 0.f, s1 = 0.f;
+      for (int r = 0; r < rows; ++r) {
+        const float* row = st + r * W;
+        float t = 0.f;
+        for (int w = ws; w < we; ++w) t += row[w];
+        if (r & 1) s1 += t; else s0 += t;
+      }
+      pooled[c * (pw + 1) + j] = (s0 + s1) / (float)(rows * (we - ws));
+    }
+    __syncwarp();                                           // every lane is done with this stage
+    if (k + 2 < nk) issue(k + 2);
   }
   __syncthreads();
   for (int j = warp; j < pw; j += 8) {
@@ -196,6 +281,23 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
     const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 8 * (size_t)W);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    // TMA-staged kernel: the longest window (rows) decides the stage size
+    int64_t rows_max = 0;
+    for (int64_t i = 0; i < ph; ++i) {
+      const int64_t r = ((i + 1) * H + ph - 1) / ph - (i * H) / ph;
+      if (r > rows_max) rows_max = r;
+    }
+    const int64_t stage_floats = ((rows_max * W + 31) / 32) * 32;
+    const size_t smem_tma = sizeof(float) * ((((size_t)C * (pw + 1) + 31) & ~(size_t)31) + 32 + 16 * (size_t)stage_floats);
+    static const bool no_tma = getenv("SPCL_DENSE_NO_TMA") != nullptr;      // A/B switch for tools/gpu_dense_bench.py
+    if (vec4 && !no_tma && rows_max * W * 4 >= 1024 && smem_tma <= 200 * 1024) {
+      SPCL_CUDA_TRY(cudaFuncSetAttribute(dense::pool_rows_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_tma));
+      dense::pool_rows_fwd_tma<<<(unsigned)(B * ph), 256, smem_tma, s>>>(x, y, inv_norm, (int)C, (int)H, (int)W,
+                                                                        (int)ph, (int)pw, eps, (int)stage_floats);
+      SPCL_LAUNCH_CHECK("spcl_dense_rows_fwd/tma");
+      return SPCL_OK;
+    }
     auto kern = vec4 ? dense::pool_rows_fwd<true> : dense::pool_rows_fwd<false>;
     if (smem > 48 * 1024)
       SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

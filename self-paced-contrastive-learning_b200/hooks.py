@@ -227,7 +227,7 @@ class INFONCEEpochHook:
     def _figures(self):
         if self._n == 0 and self._figure_fn is not None:          # :188-192, first batch of the epoch only
             for tag in ("pos_mask", "sim_exp", "sim_logits"):
-                self._figure_fn(getattr(self._criterion, tag), tag)
+                self._figure_fn(self._criterion.figure(tag), tag)        # sub-sampled above 1024 anchors
 
     def __call__(self, features_tf: Tensor, tf_features: Tensor, *, partition_group=None, label_group=None,
                  seed: Optional[int] = None, **kwargs) -> Tensor:
@@ -276,7 +276,7 @@ class SPINFONCEEpochHook(INFONCEEpochHook):
         self.meters["sp_weight"].add(self._criterion._scalars[1])     # device scalar; no .item() per batch
         self.meters["age_param"].add(self._criterion.age_param)
         if self._n == 1 and self._figure_fn is not None:              # after the first batch (:264)
-            self._figure_fn(self._criterion.sp_mask, "sp_mask")
+            self._figure_fn(self._criterion.figure("sp_mask"), "sp_mask")
         return loss
 
 

@@ -67,6 +67,45 @@ class _Diagnostics:
         self.row_stats, self.t, self.gamma, self.mode = row_stats, temperature, gamma, mode
         self._cache = {}
 
+    def subsampled(self, name, max_side):
+        """``name`` restricted to ``max_side`` evenly spaced anchors (same rows and columns): what a figure of an
+        N x N matrix can show anyway, for any N.  ``sim_logits`` is shifted by the sub-sample's own maximum -- the
+        diagonal 1/T for unit rows, i.e. the reference's global maximum (:28-29)."""
+        n = self.z1.shape[0]
+        N = 2 * n
+        if N <= max_side:
+            return self.get(name)
+        idx = torch.linspace(0, N - 1, max_side, device=self.z1.device).round().long().unique()
+        z = torch.cat([self.z1, self.z2]).float()[idx]
+        raw = (z @ z.t()) / self.t
+        keep = 1.0 - torch.eye(idx.numel(), device=z.device)
+        if name == "sim_logits":
+            return raw - raw.max()
+        if name == "sim_exp":
+            return torch.exp(raw - raw.max())
+        h = idx % n
+        if self.tri is not None:
+            t = self.tri[h][:, h]
+            pos, neg = (t == 1).float() * keep, (t == 0).float() * keep
+        else:
+            lab = self.labels[h]
+            same = lab[:, None] == lab[None, :]
+            pos, neg = same.float() * keep, (~same).float() * keep
+        if name == "pos_mask":
+            return pos
+        if name == "neg_mask":
+            return neg
+        if name == "sp_mask":
+            l = self.row_stats[0, idx, None] - raw
+            if self.mode in (nat.MODE_NONE, nat.MODE_EXCL):
+                w = torch.ones_like(l)
+            elif self.mode == nat.MODE_HARD:
+                w = (l <= self.gamma).float()
+            else:
+                w = torch.clamp_min(1 - l / self.gamma, 0)
+            return torch.maximum(w, 1 - pos)
+        raise AttributeError(name)
+
     def _base(self):
         if "logits" not in self._cache:
             n = self.z1.shape[0]
@@ -223,6 +262,14 @@ class _FusedSupConBase(nn.Module):
         if self._diag is None:
             raise AttributeError(f"{name} is only available after a forward call")
         return self._diag.get(name)
+
+    def figure(self, name: str, max_side: int = 1024) -> Tensor:
+        """One of ``sim_exp / sim_logits / pos_mask / neg_mask / sp_mask`` of the last call for plotting: the full
+        matrix up to ``max_side`` anchors, an evenly sub-sampled one above (works at any N; the attribute forms
+        below materialise the full N x N matrix like the reference and refuse beyond N = 16384)."""
+        if self._diag is None:
+            raise AttributeError(f"{name} is only available after a forward call")
+        return self._diag.subsampled(name, int(max_side))
 
     sim_exp = property(lambda self: self._diag_get("sim_exp"))
     sim_logits = property(lambda self: self._diag_get("sim_logits"))

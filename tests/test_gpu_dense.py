@@ -260,3 +260,27 @@ def test_grouped_launch_falls_back_to_separate_calls_for_tensor_core_sizes():
     a = spcl_b200.grouped_forward([c1], [(z1.cuda(), z2.cuda())], [lab.tolist()])[0]          # N = 2048: bf16 path
     b = c2(z1.cuda(), z2.cuda(), target=lab.tolist())
     assert a.item() == pytest.approx(b.item(), rel=1e-6)
+
+
+def test_subsampled_figures_match_the_full_diagnostics():
+    from spcl_b200.workloads import make_views
+    n = 96
+    lab = acdc_meta_labels(n)["patient"]
+    z1, z2 = make_views(lab, 64, sigma=0.7, seed=2)
+    crit = spcl_b200.SelfPacedSupConLoss(weight_update="soft", precision="fp32")
+    crit.set_gamma(6.0)
+    crit(z1.cuda(), z2.cuda(), target=lab.tolist())
+    idx = torch.linspace(0, 2 * n - 1, 50).round().long().unique().cuda()
+    for name in ("sim_exp", "sim_logits", "pos_mask", "neg_mask", "sp_mask"):
+        full = getattr(crit, name)
+        assert torch.equal(crit.figure(name, max_side=4096), full)               # small N: the full matrix
+        sub = crit.figure(name, max_side=50)
+        assert sub.shape == (idx.numel(), idx.numel())
+        assert torch.allclose(sub, full[idx][:, idx], atol=1e-5), name
+    # beyond the full-matrix limit only the figure form is available
+    big = torch.nn.functional.normalize(torch.randn(9000, 32, device="cuda"), dim=1)
+    c2 = spcl_b200.SupConLoss1()
+    c2(big, big.clone())
+    with pytest.raises(RuntimeError):
+        c2.sim_exp
+    assert c2.figure("sim_exp", 256).shape[0] <= 256
