@@ -358,7 +358,7 @@ def main():
     if world == 1:
         from spcl_b200.workloads import acdc_meta_labels, make_views
         meta = acdc_meta_labels(256)
-        def small_step(graphed, grouped=False):
+        def small_step(graphed, grouped=False, group_graph=False):
             probs = []
             for kind, gm in (("partition", 5.0), ("patient", 3.5), ("cycle", 2.0)):
                 c = spcl_b200.SelfPacedSupConLoss(weight_update="soft", correct_grad=True, check_nan=False,
@@ -371,7 +371,7 @@ def main():
                 for _, p1, p2, _lb in probs:
                     p1.grad = p2.grad = None
                 ls = spcl_b200.grouped_forward([q[0] for q in probs], [(q[1], q[2]) for q in probs],
-                                               [q[3] for q in probs])
+                                               [q[3] for q in probs], cuda_graph=group_graph)
                 (ls[0] + ls[1] + ls[2]).backward()
             def run():
                 if grouped:
@@ -392,7 +392,8 @@ def main():
             return (time.perf_counter() - t0) / 100 * 1e6
         small = {"workload": "cfg2: 3 meta-label problems, N = 512, d = 256, fp32 path, fwd+bwd of all three",
                  "eager_us_per_step": small_step(False), "cuda_graph_us_per_step": small_step(True),
-                 "grouped_launch_us_per_step": small_step(False, grouped=True)}
+                 "grouped_launch_us_per_step": small_step(False, grouped=True),
+                 "grouped_graph_us_per_step": small_step(False, grouped=True, group_graph=True)}
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None

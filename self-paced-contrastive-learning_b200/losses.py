@@ -326,13 +326,17 @@ class SelfPacedSupConLoss(_FusedSupConBase):
     sp_mask = property(lambda self: self._diag_get("sp_mask"))
 
 
-def grouped_forward(criteria, feats, targets=None):
+_GROUP_GRAPHS: dict = {}
+
+
+def grouped_forward(criteria, feats, targets=None, cuda_graph: bool = False):
     """The K contrastive losses of one training step -- one criterion, projector output pair and label list per
     meta-label (partition / patient / cycle; poster Eq. 4, ``semi_seg`` ``creator.py:102-124``) -- evaluated with ONE
     kernel launch per stage for the whole group instead of K separate forward calls.  Equivalent to
     ``[c(z1, z2, target=t) for c, (z1, z2), t in zip(criteria, feats, targets)]`` (same losses, gradients,
     ``downgrade_ratio``); problems the grouped fp32 kernels do not carry (tensor-core sizes, ``exclude_other_pos``)
-    make the whole group run as those separate calls.  The N x N diagnostics are not kept for grouped calls."""
+    make the whole group run as those separate calls.  The N x N diagnostics are not kept for grouped calls.
+    ``cuda_graph=True`` replays forward + backward of the whole group as one captured graph (per shapes / gammas)."""
     K = len(criteria)
     targets = [None] * K if targets is None else list(targets)
     if len(feats) != K or len(targets) != K:
@@ -352,8 +356,18 @@ def grouped_forward(criteria, feats, targets=None):
     for (z1, _), t in zip(feats, targets):
         n, dev = z1.shape[0], z1.device
         lab = ops.label_codes(t, n, dev) if t is not None else torch.arange(n, dtype=torch.int32, device=dev)
-        labels.append(lab.repeat(2))
-    scalars = ops.supcon_group_f32(list(feats), labels, metas)
+        labels.append(lab if cuda_graph else lab.repeat(2))
+    if cuda_graph:
+        shapes = [tuple(z1.shape) for z1, _ in feats]
+        key = (str(feats[0][0].device), tuple(shapes), tuple((float(t), float(g), int(m), bool(c)) for t, g, m, c in metas))
+        runner = _GROUP_GRAPHS.get(key)
+        if runner is None:
+            if len(_GROUP_GRAPHS) >= 8:               # gammas change once per epoch: keep the cache small
+                _GROUP_GRAPHS.pop(next(iter(_GROUP_GRAPHS)))
+            runner = _GROUP_GRAPHS[key] = ops.GroupGraphRunner(shapes, metas, feats[0][0].device)
+        scalars = list(ops.supcon_group_f32_graphed(list(feats), labels, runner).unbind(0))
+    else:
+        scalars = ops.supcon_group_f32(list(feats), labels, metas)
     out = []
     for crit, sc in zip(criteria, scalars):
         crit._scalars, crit._ratio_cache, crit._diag = sc.detach(), None, None

@@ -606,3 +606,84 @@ def supcon_group_f32(views, labels, meta):
             raise TypeError("labels must be int32[2n]")
         flat += [z1.float().contiguous(), z2.float().contiguous()]
     return list(_GroupSupCon.apply(tuple(meta), tuple(labels), *flat))
+
+
+class GroupGraphRunner:
+    """Grouped forward + backward (upstream gradients of 1) of K fp32 label-form problems as ONE CUDA-graph replay, for
+    fixed shapes and hyper-parameters: 7 kernels per training step's losses instead of K x 13 launches.  Inputs are
+    copied into static buffers with two ``_foreach_copy_`` calls; outputs live in static buffers until the next run."""
+
+    def __init__(self, shapes, meta, device):
+        self.shapes, self.meta, self.K = list(shapes), list(meta), len(shapes)
+        g = torch.Generator(device="cpu").manual_seed(0)
+        self.z, self.lab, self.dz = [], [], []
+        total = 0
+        for n, d in self.shapes:
+            warm = torch.nn.functional.normalize(torch.randn(2 * n, d, generator=g), dim=1).to(device)
+            self.z.append(warm.contiguous())
+            self.lab.append(torch.arange(2 * n, dtype=torch.int32, device=device) % n)
+            self.dz.append(torch.empty(2 * n, d, dtype=torch.float32, device=device))
+            total += 2 * n * 8 + 8
+        self.ws = torch.empty(total, dtype=torch.float32, device=device)
+        self.scalars = torch.empty(self.K, 4, dtype=torch.float32, device=device)
+        self.ones = torch.ones(1, dtype=torch.float32, device=device)
+        self.probs = (nat.ProblemF32 * self.K)()
+        off = 0
+        for k, ((n, d), (temperature, gamma, mode, cg)) in enumerate(zip(self.shapes, self.meta)):
+            N, q, base = 2 * n, self.probs[k], self.ws[off:]
+            off += N * 8 + 8
+            q.z, q.n_total, q.d, q.ldz, q.labels = self.z[k].data_ptr(), N, d, d, self.lab[k].data_ptr()
+            q.inv_tau, q.gamma, q.mode, q.correct_grad = 1.0 / float(temperature), float(gamma), int(mode), int(bool(cg))
+            q.acc, q.row_stats, q.stats_stride = base.data_ptr(), base[N * 4:].data_ptr(), N
+            q.partials, q.scalars = base[N * 8:].data_ptr(), self.scalars[k].data_ptr()
+            q.grad_out, q.dz, q.lddz = self.ones.data_ptr(), self.dz[k].data_ptr(), d
+        # destination views of the per-step input copies: z1 | z2 halves, labels twice
+        self.z_dst = [h for (n, _), z in zip(self.shapes, self.z) for h in (z[:n], z[n:])]
+        self.lab_dst = [h for (n, _), l in zip(self.shapes, self.lab) for h in (l[:n], l[n:])]
+
+        def body():
+            st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(self.probs), self.K, st)
+            nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(self.probs), self.K, st)
+
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def run(self, flat_views, labels):
+        torch._foreach_copy_(self.z_dst, list(flat_views))
+        torch._foreach_copy_(self.lab_dst, [l for l in labels for _ in (0, 1)])
+        self.graph.replay()
+        return self.scalars, self.dz
+
+
+class _GroupGraphed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, labels, *views):
+        scalars, dz = runner.run([v.detach() for v in views], labels)
+        ctx.dz = [t.clone() for t in dz]                 # the runner's buffers belong to its next replay
+        ctx.ns = [n for n, _ in runner.shapes]
+        return scalars.clone()
+
+    @staticmethod
+    def backward(ctx, g_scalars):
+        grads = []
+        for k, (dz, n) in enumerate(zip(ctx.dz, ctx.ns)):
+            dz = dz * g_scalars[k, 0]
+            grads += [dz[:n], dz[n:]]
+        return (None, None, *grads)
+
+
+def supcon_group_f32_graphed(views, labels, runner: GroupGraphRunner):
+    """``labels``: per problem int32 [n] (one view; tiled inside).  -> scalars [K, 4]."""
+    flat = []
+    for (z1, z2) in views:
+        _require_cuda(z1, z2)
+        flat += [z1.float(), z2.float()]
+    return _GroupGraphed.apply(runner, tuple(labels), *flat)

@@ -21,7 +21,7 @@ ncu --set full --clock-control none --import-source on -k regex:bwd_kernel -s 3 
 ncu --set full --clock-control none --import-source on -k regex:stats_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_fwd \
     python bench.py --steps 2 --warmup 3 --skip-cpu-baseline > gpurun_out/${TAG}_ncu_fwd.log 2>&1
 python tools/gpu_dense_bench.py > gpurun_out/${TAG}_dense_bench.json 2> gpurun_out/${TAG}_dense_bench.err
-ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 8 -f -o gpurun_out/${TAG}_prof_dense \
+ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 30 -f -o gpurun_out/${TAG}_prof_dense \
     python tools/gpu_dense_bench.py > gpurun_out/${TAG}_ncu_dense.log 2>&1
 python tools/cfg5_step.py > gpurun_out/${TAG}_cfg5.json 2> gpurun_out/${TAG}_cfg5.err
 fi

@@ -60,7 +60,7 @@ def dense(tag):
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
-    out = [f"# ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 8  python tools/gpu_dense_bench.py  ({rep.name})",
+    out = [f"# ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 30  python tools/gpu_dense_bench.py  ({rep.name})",
            "# algorithmic bytes at this shape: fwd 4*B*C*H*W + 4*B*ph*pw*C = 839 MB; bwd 4*B*C*H*W written + 17 MB of rows read"]
     seen = set()
     for r in rows[2:]:
