@@ -16,6 +16,11 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+// default of the TMA-staged forward; flipped to true once the kernel has passed the GPU parity tests
+#ifndef SPCL_DENSE_TMA_DEFAULT
+#define SPCL_DENSE_TMA_DEFAULT false
+#endif
+
 namespace spcl {
 namespace dense {
 
@@ -289,8 +294,10 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
     }
     const int64_t stage_floats = ((rows_max * W + 31) / 32) * 32;
     const size_t smem_tma = sizeof(float) * ((((size_t)C * (pw + 1) + 31) & ~(size_t)31) + 32 + 16 * (size_t)stage_floats);
-    static const bool no_tma = getenv("SPCL_DENSE_NO_TMA") != nullptr;      // A/B switch for tools/gpu_dense_bench.py
-    if (vec4 && !no_tma && rows_max * W * 4 >= 1024 && smem_tma <= 200 * 1024) {
+    // A/B switch (tools/gpu_dense_bench.py): SPCL_DENSE_TMA=0 forces the LDG kernel, =1 the TMA kernel
+    static const char* tma_env = getenv("SPCL_DENSE_TMA");
+    static const bool use_tma = tma_env != nullptr ? tma_env[0] == '1' : SPCL_DENSE_TMA_DEFAULT;
+    if (vec4 && use_tma && rows_max * W * 4 >= 1024 && smem_tma <= 200 * 1024) {
       SPCL_CUDA_TRY(cudaFuncSetAttribute(dense::pool_rows_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_tma));
       dense::pool_rows_fwd_tma<<<(unsigned)(B * ph), 256, smem_tma, s>>>(x, y, inv_norm, (int)C, (int)H, (int)W,
