@@ -35,7 +35,7 @@ constexpr int kMaxW = 1024;    // per-warp column-sum staging (floats)
 // window's input rows coalesced along W, keeps per-column sums in shared memory, and its lanes reduce the
 // W windows.  The C x pw pooled values of the CTA are normalised over C and written as rows
 // y[(b*ph + i)*pw + j][0..C).
-// dynamic shared memory: C * (pw + 1) floats (pooled) + 8 * W floats (column sums)
+// dynamic shared memory: C * (pw + 1) floats (pooled) + 16 * W floats (column sums, 2 channels per warp)
 // ------------------------------------------------------------------------------------------------
 template <bool VEC4>
 __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x, float* __restrict__ y,
@@ -43,52 +43,61 @@ __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x
                                                      int pw, float eps) {
   extern __shared__ float smem[];
   float* pooled = smem;                                  // [C][pw + 1]
-  float* colsum = smem + (((size_t)C * (pw + 1) + 3) & ~(size_t)3);   // [8][W], 16-byte aligned
+  float* colsum = smem + (((size_t)C * (pw + 1) + 3) & ~(size_t)3);   // [8 warps][2][W], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / ph, i = blockIdx.x % ph;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
-  float* cs = colsum + (size_t)warp * W;
-  for (int c = warp; c < C; c += 8) {
-    const float* xc = x + ((int64_t)b * C + c) * H * W;
+  // two channels (c, c + 8) per iteration: two independent load -> add chains double the loads in flight per lane
+  // (ptxas keeps only ~2 outstanding per chain, whatever the unrolling)
+  float* csa = colsum + (size_t)warp * 2 * W;
+  float* csb = csa + W;
+  for (int c = warp; c < C; c += 16) {
+    const bool has2 = c + 8 < C;
+    const float* xa = x + ((int64_t)b * C + c) * H * W;
+    const float* xb = has2 ? xa + (int64_t)8 * H * W : xa;
     if (VEC4) {                      // W % 4 == 0 and x 16-byte aligned: 16-byte loads, 4 columns per lane
-      const float4* x4 = reinterpret_cast<const float4*>(xc);
+      const float4* a4 = reinterpret_cast<const float4*>(xa);
+      const float4* b4 = reinterpret_cast<const float4*>(xb);
       const int W4 = W >> 2;
       for (int w4 = lane; w4 < W4; w4 += 32) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        // predicated batches of 8 rows: every load of a batch is in flight before the first add (a runtime-trip
-        // unroll leaves a serial remainder loop: 4 DRAM round trips for a 7-row window instead of 1)
-        for (int h0 = hs; h0 < he; h0 += 8) {
-          float4 v[8];
+        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+        for (int h0 = hs; h0 < he; h0 += 4) {
+          float4 va[4], vb[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k)       // unconditional loads (row index clamped): ptxas batches them
-            v[k] = __ldg(x4 + (int64_t)min(h0 + k, he - 1) * W4 + w4);
+          for (int k = 0; k < 4; ++k) {           // row index clamped: unconditional, independent loads
+            const int64_t off = (int64_t)min(h0 + k, he - 1) * W4 + w4;
+            va[k] = __ldg(a4 + off);
+            vb[k] = __ldg(b4 + off);
+          }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             const float m = (h0 + k < he) ? 1.f : 0.f;
-            s.x = fmaf(m, v[k].x, s.x); s.y = fmaf(m, v[k].y, s.y); s.z = fmaf(m, v[k].z, s.z); s.w = fmaf(m, v[k].w, s.w);
+            sa.x = fmaf(m, va[k].x, sa.x); sa.y = fmaf(m, va[k].y, sa.y); sa.z = fmaf(m, va[k].z, sa.z); sa.w = fmaf(m, va[k].w, sa.w);
+            sb.x = fmaf(m, vb[k].x, sb.x); sb.y = fmaf(m, vb[k].y, sb.y); sb.z = fmaf(m, vb[k].z, sb.z); sb.w = fmaf(m, vb[k].w, sb.w);
           }
         }
-        reinterpret_cast<float4*>(cs)[w4] = s;
+        reinterpret_cast<float4*>(csa)[w4] = sa;
+        reinterpret_cast<float4*>(csb)[w4] = sb;
       }
     } else {
       for (int w = lane; w < W; w += 32) {
-        float s = 0.f;
-        for (int h0 = hs; h0 < he; h0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = __ldg(xc + (int64_t)min(h0 + k, he - 1) * W + w);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) s = fmaf((h0 + k < he) ? 1.f : 0.f, v[k], s);
+        float sa = 0.f, sb = 0.f;
+        for (int h = hs; h < he; ++h) {
+          sa += __ldg(xa + (int64_t)h * W + w);
+          sb += __ldg(xb + (int64_t)h * W + w);
         }
-        cs[w] = s;
+        csa[w] = sa;
+        csb[w] = sb;
       }
     }
     __syncwarp();
     for (int j = lane; j < pw; j += 32) {
       const int ws = win_begin(j, W, pw), we = win_end(j, W, pw);
-      float s = 0.f;
-      for (int w = ws; w < we; ++w) s += cs[w];
-      pooled[c * (pw + 1) + j] = s / (float)((he - hs) * (we - ws));
+      float sa = 0.f, sb = 0.f;
+      for (int w = ws; w < we; ++w) { sa += csa[w]; sb += csb[w]; }
+      const float inv_area = 1.f / (float)((he - hs) * (we - ws));
+      pooled[c * (pw + 1) + j] = sa * inv_area;
+      if (has2) pooled[(c + 8) * (pw + 1) + j] = sb * inv_area;
     }
     __syncwarp();
   }
@@ -179,35 +188,57 @@ __global__ void __launch_bounds__(256) pool_rows_fwd_tma(const float* __restrict
 // 1 / area and summed into G[c][j] in shared memory (the transpose), then every channel's input row is written
 // coalesced along w as G[c][j0(w)] (+ G[c][j0(w) + 1] when the next window also covers w).
 // dynamic shared memory: C * (pw + 1) floats
+template <bool VEC4>
 __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, float* __restrict__ gx, int C,
                                                      int H, int W, int ph, int pw) {
   extern __shared__ float G[];                            // [C][pw + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int i0 = (int)(((int64_t)h * ph) / H);
-  int irow[2], ilen[2], ni = 0;
+  int irow[2] = {0, 0}, ilen[2] = {1, 1}, ni = 0;
   for (int i = i0; i <= min(i0 + 1, ph - 1); ++i) {
     const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
     if (h >= hs && h < he) { irow[ni] = i; ilen[ni] = he - hs; ++ni; }
   }
+  const int stride = pw + 1;
   for (int j = warp; j < pw; j += 8) {
     const int wlen = win_end(j, W, pw) - win_begin(j, W, pw);
-    for (int c = lane; c < C; c += 32) {
-      float g = 0.f;
-      for (int k = 0; k < ni; ++k)
-        g += __ldg(gp + (((int64_t)b * ph + irow[k]) * pw + j) * C + c) / (float)(ilen[k] * wlen);
-      G[c * (pw + 1) + j] = g;
-    }
+    const float r0 = 1.f / (float)(ilen[0] * wlen), r1 = ni > 1 ? 1.f / (float)(ilen[1] * wlen) : 0.f;
+    const float* g0 = gp + (((int64_t)b * ph + irow[0]) * pw + j) * C;
+    const float* g1 = gp + (((int64_t)b * ph + irow[ni > 1 ? 1 : 0]) * pw + j) * C;
+    for (int c = lane; c < C; c += 32) G[c * stride + j] = fmaf(__ldg(g1 + c), r1, __ldg(g0 + c) * r0);
   }
   __syncthreads();
-  for (int w = lane; w < W; w += 32) {
-    const int j0 = (int)(((int64_t)w * pw) / W);
-    const bool two = (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
-    float* out = gx + (((int64_t)b * C) * H + h) * W + w;
-    for (int c = warp; c < C; c += 8) {
-      float g = G[c * (pw + 1) + j0];
-      if (two) g += G[c * (pw + 1) + j0 + 1];
-      out[(int64_t)c * H * W] = g;
+  const int64_t plane = (int64_t)H * W;
+  float* base = gx + ((int64_t)b * C * H + h) * W;
+  if (VEC4) {                                             // W % 4 == 0, gx 16-byte aligned: one 16-byte store per lane
+    for (int w4 = lane; w4 < (W >> 2); w4 += 32) {
+      int j0[4];
+      bool two[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int w = w4 * 4 + e;
+        j0[e] = (int)(((int64_t)w * pw) / W);
+        two[e] = (j0[e] + 1 < pw) && (win_begin(j0[e] + 1, W, pw) <= w);
+      }
+      float* out = base + w4 * 4;
+      const float* Gc = G + warp * stride;
+      for (int c = warp; c < C; c += 8, Gc += 8 * stride) {
+        float4 v;
+        v.x = Gc[j0[0]] + (two[0] ? Gc[j0[0] + 1] : 0.f);
+        v.y = Gc[j0[1]] + (two[1] ? Gc[j0[1] + 1] : 0.f);
+        v.z = Gc[j0[2]] + (two[2] ? Gc[j0[2] + 1] : 0.f);
+        v.w = Gc[j0[3]] + (two[3] ? Gc[j0[3] + 1] : 0.f);
+        *reinterpret_cast<float4*>(out + c * plane) = v;
+      }
+    }
+  } else {
+    for (int w = lane; w < W; w += 32) {
+      const int j0 = (int)(((int64_t)w * pw) / W);
+      const bool two = (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
+      float* out = base + w;
+      const float* Gc = G + warp * stride;
+      for (int c = warp; c < C; c += 8, Gc += 8 * stride) out[c * plane] = Gc[j0] + (two ? Gc[j0 + 1] : 0.f);
     }
   }
 }
@@ -283,7 +314,7 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (points == nullptr) {
     if (W > dense::kMaxW) return SPCL_ERR_UNSUPPORTED;
-    const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 8 * (size_t)W);
+    const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 16 * (size_t)W);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     // TMA-staged kernel: the longest window (rows) decides the stage size
@@ -329,9 +360,11 @@ extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points,
     if (B * H > INT_MAX) return SPCL_ERR_INVALID_ARG;
     const size_t smem = sizeof(float) * (size_t)C * (pw + 1);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
+    const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
+    auto kern = vec4 ? dense::pool_rows_bwd<true> : dense::pool_rows_bwd<false>;
     if (smem > 48 * 1024)
-      SPCL_CUDA_TRY(cudaFuncSetAttribute(dense::pool_rows_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense::pool_rows_bwd<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
+      SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
   } else {
     if (P <= 0 || P > INT_MAX) return SPCL_ERR_INVALID_ARG;
     SPCL_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * B * C * H * W, s));

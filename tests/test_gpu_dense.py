@@ -222,8 +222,7 @@ def test_cfg5_encoder_step_fused_vs_reference_loss():
     [(24, 64, "patient"), (100, 128, "composite"), (256, 256, "cycle"), (7, 16, "self")],   # ragged group
     [(64, 128, "partition")],
 ])
-@pytest.mark.parametrize("graph", [False, pytest.param(True, marks=pytest.mark.xfail(
-    reason="grouped CUDA-graph runner not yet confirmed on hardware (GPU pod busy when it was written)", strict=False))])
+@pytest.mark.parametrize("graph", [False, True])
 def test_grouped_launch_equals_separate_calls(shapes, graph):
     from spcl_b200.workloads import make_views
     specs = [("soft", 5.0, True), ("hard", 3.5, False), ("soft", 2.0, False), ("none", 1e6, False)]
