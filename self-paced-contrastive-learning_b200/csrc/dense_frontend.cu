@@ -20,13 +20,21 @@
 #ifndef SPCL_DENSE_TMA_DEFAULT
 #define SPCL_DENSE_TMA_DEFAULT false
 #endif
+#ifndef SPCL_DENSE_NCH_DEFAULT
+#define SPCL_DENSE_NCH_DEFAULT 2
+#endif
 
 namespace spcl {
 namespace dense {
 
 // adaptive pooling window of output index i over an input extent L split into n cells (ATen's start/end index)
-__device__ __forceinline__ int win_begin(int i, int L, int n) { return (int)(((int64_t)i * L) / n); }
-__device__ __forceinline__ int win_end(int i, int L, int n) { return (int)((((int64_t)(i + 1)) * L + n - 1) / n); }
+// 32-bit on purpose (a 64-bit division is ~100 instructions and made the backward issue-bound); the host
+// entry points reject extents with L * n > INT_MAX
+__device__ __forceinline__ int win_begin(int i, int L, int n) { return (int)(((unsigned)i * (unsigned)L) / (unsigned)n); }
+__device__ __forceinline__ int win_end(int i, int L, int n) {
+  return (int)((((unsigned)(i + 1)) * (unsigned)L + (unsigned)n - 1u) / (unsigned)n);
+}
+__device__ __forceinline__ int cell_of(int x, int L, int n) { return (int)(((unsigned)x * (unsigned)n) / (unsigned)L); }
 
 constexpr int kMaxW = 1024;    // per-warp column-sum staging (floats)
 
@@ -37,67 +45,73 @@ constexpr int kMaxW = 1024;    // per-warp column-sum staging (floats)
 // y[(b*ph + i)*pw + j][0..C).
 // dynamic shared memory: C * (pw + 1) floats (pooled) + 16 * W floats (column sums, 2 channels per warp)
 // ------------------------------------------------------------------------------------------------
-template <bool VEC4>
+template <bool VEC4, int NCH>
 __global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x, float* __restrict__ y,
                                                      float* __restrict__ inv_norm, int C, int H, int W, int ph,
                                                      int pw, float eps) {
   extern __shared__ float smem[];
   float* pooled = smem;                                  // [C][pw + 1]
-  float* colsum = smem + (((size_t)C * (pw + 1) + 3) & ~(size_t)3);   // [8 warps][2][W], 16-byte aligned
+  float* colsum = smem + (((size_t)C * (pw + 1) + 3) & ~(size_t)3);   // [8 warps][NCH][W], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / ph, i = blockIdx.x % ph;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
-  // two channels (c, c + 8) per iteration: two independent load -> add chains double the loads in flight per lane
-  // (ptxas keeps only ~2 outstanding per chain, whatever the unrolling)
-  float* csa = colsum + (size_t)warp * 2 * W;
-  float* csb = csa + W;
-  for (int c = warp; c < C; c += 16) {
-    const bool has2 = c + 8 < C;
-    const float* xa = x + ((int64_t)b * C + c) * H * W;
-    const float* xb = has2 ? xa + (int64_t)8 * H * W : xa;
+  // NCH channels (c, c + 8, ...) per iteration: NCH independent load -> add chains multiply the loads in flight per
+  // lane (ptxas keeps only ~2 outstanding per chain, whatever the unrolling)
+  float* cs = colsum + (size_t)warp * NCH * W;
+  for (int c = warp; c < C; c += 8 * NCH) {
+    const float* xc[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) xc[u] = x + ((int64_t)b * C + min(c + 8 * u, C - 1)) * H * W;   // clamped: re-read
     if (VEC4) {                      // W % 4 == 0 and x 16-byte aligned: 16-byte loads, 4 columns per lane
-      const float4* a4 = reinterpret_cast<const float4*>(xa);
-      const float4* b4 = reinterpret_cast<const float4*>(xb);
       const int W4 = W >> 2;
       for (int w4 = lane; w4 < W4; w4 += 32) {
-        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+        float4 sum[NCH];
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int h0 = hs; h0 < he; h0 += 4) {
-          float4 va[4], vb[4];
+          float4 v[4][NCH];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {           // row index clamped: unconditional, independent loads
             const int64_t off = (int64_t)min(h0 + k, he - 1) * W4 + w4;
-            va[k] = __ldg(a4 + off);
-            vb[k] = __ldg(b4 + off);
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) v[k][u] = __ldg(reinterpret_cast<const float4*>(xc[u]) + off);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float m = (h0 + k < he) ? 1.f : 0.f;
-            sa.x = fmaf(m, va[k].x, sa.x); sa.y = fmaf(m, va[k].y, sa.y); sa.z = fmaf(m, va[k].z, sa.z); sa.w = fmaf(m, va[k].w, sa.w);
-            sb.x = fmaf(m, vb[k].x, sb.x); sb.y = fmaf(m, vb[k].y, sb.y); sb.z = fmaf(m, vb[k].z, sb.z); sb.w = fmaf(m, vb[k].w, sb.w);
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+              sum[u].x = fmaf(m, v[k][u].x, sum[u].x); sum[u].y = fmaf(m, v[k][u].y, sum[u].y);
+              sum[u].z = fmaf(m, v[k][u].z, sum[u].z); sum[u].w = fmaf(m, v[k][u].w, sum[u].w);
+            }
           }
         }
-        reinterpret_cast<float4*>(csa)[w4] = sa;
-        reinterpret_cast<float4*>(csb)[w4] = sb;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) reinterpret_cast<float4*>(cs + u * W)[w4] = sum[u];
       }
     } else {
       for (int w = lane; w < W; w += 32) {
-        float sa = 0.f, sb = 0.f;
+        float sum[NCH];
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) sum[u] = 0.f;
         for (int h = hs; h < he; ++h) {
-          sa += __ldg(xa + (int64_t)h * W + w);
-          sb += __ldg(xb + (int64_t)h * W + w);
+#pragma unroll
+          for (int u = 0; u < NCH; ++u) sum[u] += __ldg(xc[u] + (int64_t)h * W + w);
         }
-        csa[w] = sa;
-        csb[w] = sb;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) cs[u * W + w] = sum[u];
       }
     }
     __syncwarp();
     for (int j = lane; j < pw; j += 32) {
       const int ws = win_begin(j, W, pw), we = win_end(j, W, pw);
-      float sa = 0.f, sb = 0.f;
-      for (int w = ws; w < we; ++w) { sa += csa[w]; sb += csb[w]; }
       const float inv_area = 1.f / (float)((he - hs) * (we - ws));
-      pooled[c * (pw + 1) + j] = sa * inv_area;
-      if (has2) pooled[(c + 8) * (pw + 1) + j] = sb * inv_area;
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        float t = 0.f;
+        for (int w = ws; w < we; ++w) t += cs[u * W + w];
+        if (c + 8 * u < C) pooled[(c + 8 * u) * (pw + 1) + j] = t * inv_area;
+      }
     }
     __syncwarp();
   }
@@ -194,7 +208,7 @@ __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ g
   extern __shared__ float G[];                            // [C][pw + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int i0 = (int)(((int64_t)h * ph) / H);
+  const int i0 = cell_of(h, H, ph);
   int irow[2] = {0, 0}, ilen[2] = {1, 1}, ni = 0;
   for (int i = i0; i <= min(i0 + 1, ph - 1); ++i) {
     const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ g
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int w = w4 * 4 + e;
-        j0[e] = (int)(((int64_t)w * pw) / W);
+        j0[e] = cell_of(w, W, pw);
         two[e] = (j0[e] + 1 < pw) && (win_begin(j0[e] + 1, W, pw) <= w);
       }
       float* out = base + w4 * 4;
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ g
     }
   } else {
     for (int w = lane; w < W; w += 32) {
-      const int j0 = (int)(((int64_t)w * pw) / W);
+      const int j0 = cell_of(w, W, pw);
       const bool two = (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
       float* out = base + w;
       const float* Gc = G + warp * stride;
@@ -302,7 +316,8 @@ using namespace spcl;
 
 static bool dense_args_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t ph, int64_t pw) {
   return B > 0 && C > 0 && H > 0 && W > 0 && ph > 0 && pw > 0 && C <= INT_MAX && H <= INT_MAX && W <= INT_MAX &&
-         B * ph <= INT_MAX && B * C * H * W / H / W == B * C;
+         B * ph <= INT_MAX && B * C * H * W / H / W == B * C && (H + 1) * (ph + 1) <= INT_MAX &&
+         (W + 1) * (pw + 1) <= INT_MAX;      // window arithmetic is 32-bit on the device
 }
 
 extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
@@ -314,8 +329,6 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (points == nullptr) {
     if (W > dense::kMaxW) return SPCL_ERR_UNSUPPORTED;
-    const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 16 * (size_t)W);
-    if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     // TMA-staged kernel: the longest window (rows) decides the stage size
     int64_t rows_max = 0;
@@ -336,7 +349,15 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
       SPCL_LAUNCH_CHECK("spcl_dense_rows_fwd/tma");
       return SPCL_OK;
     }
-    auto kern = vec4 ? dense::pool_rows_fwd<true> : dense::pool_rows_fwd<false>;
+    // channels per warp iteration: 4 when the column-sum staging stays small (more loads in flight), else 2;
+    // SPCL_DENSE_NCH=2|4 overrides (A/B in tools/gpu_dense_bench.py)
+    static const char* nch_env = getenv("SPCL_DENSE_NCH");
+    int nch = SPCL_DENSE_NCH_DEFAULT;
+    if (nch_env != nullptr && (nch_env[0] == '2' || nch_env[0] == '4')) nch = nch_env[0] - '0';
+    auto kern = vec4 ? (nch == 4 ? dense::pool_rows_fwd<true, 4> : dense::pool_rows_fwd<true, 2>)
+                     : (nch == 4 ? dense::pool_rows_fwd<false, 4> : dense::pool_rows_fwd<false, 2>);
+    const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 8 * (size_t)nch * (size_t)W);
+    if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     if (smem > 48 * 1024)
       SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)(B * ph), 256, smem, s>>>(x, y, inv_norm, (int)C, (int)H, (int)W, (int)ph, (int)pw, eps);
