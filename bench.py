@@ -395,6 +395,24 @@ def main():
                  "grouped_launch_us_per_step": small_step(False, grouped=True),
                  "grouped_graph_us_per_step": small_step(False, grouped=True, group_graph=True)}
 
+    # ---------------- dense front end, secondary figure: HBM-bound kernels ----------------
+    dense_fe = None
+    if world == 1:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gpu_dense_bench", os.path.join(os.path.dirname(
+            os.path.abspath(__file__)), "tools", "gpu_dense_bench.py"))
+        try:                                        # a secondary figure must not take the headline down with it
+            gdb = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(gdb)
+            r = gdb.measure(cases=gdb.CASES[:1], reps=10)
+            c = r["cases"][0]
+              dense_fe = {"workload": "DenseProjectionHead tail: 32 x 128 x 224 x 224 -> 32 x 32 pooled, normalised rows",
+                        "bound": "hbm", "peak": r["peak_gbs"], "unit": "GB/s", "fwd_ms": c["fwd_ms"], "bwd_ms": c["bwd_ms"],
+                        "fwd_achieved": c["fwd_gbs"], "fwd_frac": c["fwd_frac"], "bwd_achieved": c["bwd_gbs"],
+                        "bwd_frac": c["bwd_frac"], "l2": c["l2"]}
+        except Exception as e:
+            dense_fe = {"error": f"{type(e).__name__}: {e}"}
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
@@ -410,7 +428,7 @@ def main():
             "config": {"workload": workload, "anchors_N": N, "d": d, "rows_per_gpu": rows,
                        "hyper": {"tau": TAU, "gamma": GAMMA, "mode": MODE_NAME, "labels": spec["labels"]},
                        "l2": "256 MB flush between timed steps", "parallelism": f"row-shard x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "small_batch": small, "gpu_launches": 6 * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "small_batch": small, "dense_front_end": dense_fe, "gpu_launches": 6 * args.steps,
             "clocks": clocks, "loss": loss_val,
         }
         print(json.dumps(line), flush=True)

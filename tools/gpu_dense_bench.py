@@ -29,22 +29,32 @@ def timed(fn, reps=10, flush_l2=True):
     return ms[len(ms) // 2]
 
 
-out = []
-for (B, C, H, W, ph, pw, P) in [(32, 128, 224, 224, 32, 32, None), (32, 128, 64, 64, 32, 32, None),
-                                (32, 128, 32, 32, 32, 32, None), (128, 128, 56, 56, 10, 10, 5)]:
-    x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
-    pts = None if P is None else spcl_b200.point_coordinates(B, ph, pw, P, seed=0).cuda()
-    rows = spcl_b200.ops.dense_rows(x, (ph, pw), pts)
-    gy = torch.randn_like(rows)
-    # inputs several times the 126 MB L2 need no flush (and a flush leaves 126 MB of dirty lines to write back
-    # inside the timed kernel); smaller ones are flushed
-    big = x.numel() * 4 > (512 << 20)
-    f_ms = timed(lambda: spcl_b200.ops.dense_rows(x.detach(), (ph, pw), pts), flush_l2=not big)
-    b_ms = timed(lambda: torch.autograd.grad(rows, x, gy, retain_graph=True), flush_l2=not big)
-    n_rows = rows.shape[0]
-    fwd_bytes = 4 * (B * C * H * W if P is None else n_rows * C * (H // ph + 1) * (W // pw + 1)) + 4 * n_rows * C
-    bwd_bytes = 4 * B * C * H * W + 3 * 4 * n_rows * C
-    out.append(dict(shape=[B, C, H, W], pooled=[ph, pw], points=P, l2="input > 4 x L2, no flush" if big else "256 MB flush", fwd_ms=f_ms, bwd_ms=b_ms,
-                    fwd_gbs=fwd_bytes / f_ms / 1e6, bwd_gbs=bwd_bytes / b_ms / 1e6,
-                    fwd_frac=fwd_bytes / f_ms / 1e6 / PEAK, bwd_frac=bwd_bytes / b_ms / 1e6 / PEAK))
-print(json.dumps(dict(peak_gbs=PEAK, cases=out)))
+CASES = [(32, 128, 224, 224, 32, 32, None), (32, 128, 64, 64, 32, 32, None), (32, 128, 32, 32, 32, 32, None),
+         (128, 128, 56, 56, 10, 10, 5)]
+
+
+def measure(cases=CASES, reps=10):
+    out = []
+    for (B, C, H, W, ph, pw, P) in cases:
+        x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+        pts = None if P is None else spcl_b200.point_coordinates(B, ph, pw, P, seed=0).cuda()
+        rows = spcl_b200.ops.dense_rows(x, (ph, pw), pts)
+        gy = torch.randn_like(rows)
+        # inputs several times the 126 MB L2 need no flush (and a flush leaves 126 MB of dirty lines to write back
+        # inside the timed kernel); smaller ones are flushed
+        big = x.numel() * 4 > (512 << 20)
+        f_ms = timed(lambda: spcl_b200.ops.dense_rows(x.detach(), (ph, pw), pts), reps, flush_l2=not big)
+        b_ms = timed(lambda: torch.autograd.grad(rows, x, gy, retain_graph=True), reps, flush_l2=not big)
+        n_rows = rows.shape[0]
+        fwd_bytes = 4 * (B * C * H * W if P is None else n_rows * C * (H // ph + 1) * (W // pw + 1)) + 4 * n_rows * C
+        bwd_bytes = 4 * B * C * H * W + 3 * 4 * n_rows * C
+        out.append(dict(shape=[B, C, H, W], pooled=[ph, pw], points=P,
+                        l2="input > 4 x L2, no flush" if big else "256 MB flush", fwd_ms=f_ms, bwd_ms=b_ms,
+                        fwd_gbs=fwd_bytes / f_ms / 1e6, bwd_gbs=bwd_bytes / b_ms / 1e6,
+                        fwd_frac=fwd_bytes / f_ms / 1e6 / PEAK, bwd_frac=bwd_bytes / b_ms / 1e6 / PEAK))
+        del x, rows, gy
+    return dict(peak_gbs=PEAK, cases=out)
+
+
+if __name__ == "__main__":
+    print(json.dumps(measure()))

@@ -23,8 +23,10 @@ ncu --set full --clock-control none --import-source on -k regex:stats_kernel -s 
 python tools/gpu_dense_bench.py > gpurun_out/${TAG}_dense_bench.json 2> gpurun_out/${TAG}_dense_bench.err
 SPCL_DENSE_TMA=0 python tools/gpu_dense_bench.py > gpurun_out/${TAG}_dense_bench_ldg.json 2>> gpurun_out/${TAG}_dense_bench.err
 SPCL_DENSE_TMA=1 python tools/gpu_dense_bench.py > gpurun_out/${TAG}_dense_bench_tma.json 2>> gpurun_out/${TAG}_dense_bench.err
-ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 30 -f -o gpurun_out/${TAG}_prof_dense \
-    python tools/gpu_dense_bench.py > gpurun_out/${TAG}_ncu_dense.log 2>&1
+for W in fwd bwd; do
+ncu --set full --clock-control none --import-source on -k regex:pool_rows_${W} -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_dense_${W} \
+    python tools/gpu_dense_bench.py > gpurun_out/${TAG}_ncu_dense_${W}.log 2>&1
+done
 python tools/cfg5_step.py > gpurun_out/${TAG}_cfg5.json 2> gpurun_out/${TAG}_cfg5.err
 SPCL_DENSE_TMA=1 timeout 300 python -m pytest tests/test_gpu_dense.py -m gpu -q > gpurun_out/${TAG}_pytest_tma.log 2>&1; echo "pytest(tma) rc=$?" | tee -a gpurun_out/${TAG}_pytest_tma.log
 fi

@@ -54,24 +54,25 @@ def full(tag, which):
 
 def dense(tag):
     """first launch of each dense front-end kernel in the capture (32 x 128 x 224 x 224 -> 32 x 32)."""
-    rep = ROOT / "gpurun_out" / f"{tag}_prof_dense.ncu-rep"
-    if not rep.exists():
+    reps = [r for r in (ROOT / "gpurun_out" / f"{tag}_prof_dense{sfx}.ncu-rep" for sfx in ("", "_fwd", "_bwd")) if r.exists()]
+    if not reps:
         return
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr = rows[0]
-    out = [f"# ncu --set full --clock-control none --import-source on -k regex:pool_rows -c 30  python tools/gpu_dense_bench.py  ({rep.name})",
-           "# algorithmic bytes at this shape: fwd 4*B*C*H*W + 4*B*ph*pw*C = 839 MB; bwd 4*B*C*H*W written + 17 MB of rows read"]
+    out = ["# ncu --set full --clock-control none --import-source on -k regex:pool_rows_{fwd,bwd} -s 3 -c 1  python tools/gpu_dense_bench.py",
+           "# shape 32 x 128 x 224 x 224 -> 32 x 32; algorithmic bytes: fwd 4*B*C*H*W + 4*B*ph*pw*C = 839 MB; bwd 4*B*C*H*W written + 17 MB of rows read"]
     seen = set()
-    for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")]
-        if name in seen:
-            continue
-        seen.add(name)
-        out.append(f"## {name}")
-        for m in METRICS:
-            if m in hdr:
-                out.append(f"{m:75s} {r[hdr.index(m)]}  {rows[1][hdr.index(m)]}")
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr = rows[0]
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            if name in seen:
+                continue
+            seen.add(name)
+            out.append(f"## {name}")
+            for m in METRICS:
+                if m in hdr:
+                    out.append(f"{m:75s} {r[hdr.index(m)]}  {rows[1][hdr.index(m)]}")
     (OUT / f"{tag}_ncu_dense.txt").write_text("\n".join(out) + "\n")
 
 
