@@ -406,7 +406,7 @@ def main():
             spec.loader.exec_module(gdb)
             r = gdb.measure(cases=gdb.CASES[:1], reps=10)
             c = r["cases"][0]
-              dense_fe = {"workload": "DenseProjectionHead tail: 32 x 128 x 224 x 224 -> 32 x 32 pooled, normalised rows",
+            dense_fe = {"workload": "DenseProjectionHead tail: 32 x 128 x 224 x 224 -> 32 x 32 pooled, normalised rows",
                         "bound": "hbm", "peak": r["peak_gbs"], "unit": "GB/s", "fwd_ms": c["fwd_ms"], "bwd_ms": c["bwd_ms"],
                         "fwd_achieved": c["fwd_gbs"], "fwd_frac": c["fwd_frac"], "bwd_achieved": c["bwd_gbs"],
                         "bwd_frac": c["bwd_frac"], "l2": c["l2"]}
