@@ -284,3 +284,23 @@ def test_group_abi_validates_arguments_without_touching_the_gpu():
     import spcl_b200
     with pytest.raises(ValueError):
         spcl_b200.grouped_forward([spcl_b200.SupConLoss1()], [], None)
+
+
+def test_dense_tail_rejects_what_is_not_on_the_hot_path():
+    import spcl_b200
+    with pytest.raises(NotImplementedError):
+        spcl_b200.DenseProjectionTail((16, 16), pool_name="adaptive_max")
+    with pytest.raises(NotImplementedError):
+        spcl_b200.DenseProjectionTail((16, 16), normalize=False)
+    assert spcl_b200.DenseProjectionTail((10, 10))._spatial_size == (10, 10)
+
+
+def test_point_coordinates_are_distinct_rows_and_columns_per_image():
+    """infonce.py:20-22 draws n rows and n columns without replacement: no two points of an image share either."""
+    import spcl_b200
+    pts = spcl_b200.point_coordinates(16, 10, 12, 5, seed=9).numpy()
+    assert pts.min() >= 0 and pts.max() < 120
+    for row in pts:
+        assert len(set(row // 12)) == 5 and len(set(row % 12)) == 5
+    with pytest.raises(ValueError):
+        spcl_b200.point_coordinates(1, 4, 4, 5, seed=0)            # more points than rows: numpy refuses, like the reference
