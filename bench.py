@@ -399,11 +399,11 @@ def main():
     dense_fe = None
     if world == 1:
         import importlib.util
-        spec = importlib.util.spec_from_file_location("gpu_dense_bench", os.path.join(os.path.dirname(
+        mod_spec = importlib.util.spec_from_file_location("gpu_dense_bench", os.path.join(os.path.dirname(
             os.path.abspath(__file__)), "tools", "gpu_dense_bench.py"))
         try:                                        # a secondary figure must not take the headline down with it
-            gdb = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(gdb)
+            gdb = importlib.util.module_from_spec(mod_spec)
+            mod_spec.loader.exec_module(gdb)
             r = gdb.measure(cases=gdb.CASES[:1], reps=10)
             c = r["cases"][0]
             dense_fe = {"workload": "DenseProjectionHead tail: 32 x 128 x 224 x 224 -> 32 x 32 pooled, normalised rows",
