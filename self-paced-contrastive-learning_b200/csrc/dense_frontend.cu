@@ -45,8 +45,8 @@ constexpr int kMaxW = 1024;    // per-warp column-sum staging (floats)
 // y[(b*ph + i)*pw + j][0..C).
 // dynamic shared memory: C * (pw + 1) floats (pooled) + 16 * W floats (column sums, 2 channels per warp)
 // ------------------------------------------------------------------------------------------------
-template <bool VEC4, int NCH>
-__global__ void __launch_bounds__(256) pool_rows_fwd(const float* __restrict__ x, float* __restrict__ y,
+template <bool VEC4, int NCH, int MINB>
+__global__ void __launch_bounds__(256, MINB) pool_rows_fwd(const float* __restrict__ x, float* __restrict__ y,
                                                      float* __restrict__ inv_norm, int C, int H, int W, int ph,
                                                      int pw, float eps) {
   extern __shared__ float smem[];
@@ -202,25 +202,33 @@ __global__ void __launch_bounds__(256) pool_rows_fwd_tma(const float* __restrict
 // 1 / area and summed into G[c][j] in shared memory (the transpose), then every channel's input row is written
 // coalesced along w as G[c][j0(w)] (+ G[c][j0(w) + 1] when the next window also covers w).
 // dynamic shared memory: C * (pw + 1) floats
-template <bool VEC4>
+// EXACT: H % ph == 0 and W % pw == 0 -- every pixel lies in exactly one window of constant size
+template <bool VEC4, bool EXACT>
 __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, float* __restrict__ gx, int C,
                                                      int H, int W, int ph, int pw) {
   extern __shared__ float G[];                            // [C][pw + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int i0 = cell_of(h, H, ph);
-  int irow[2] = {0, 0}, ilen[2] = {1, 1}, ni = 0;
-  for (int i = i0; i <= min(i0 + 1, ph - 1); ++i) {
-    const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
-    if (h >= hs && h < he) { irow[ni] = i; ilen[ni] = he - hs; ++ni; }
+  int irow[2] = {i0, i0}, ilen[2] = {H / ph, 1}, ni = 1;
+  if (!EXACT) {
+    ni = 0;
+    for (int i = i0; i <= min(i0 + 1, ph - 1); ++i) {
+      const int hs = win_begin(i, H, ph), he = win_end(i, H, ph);
+      if (h >= hs && h < he) { irow[ni] = i; ilen[ni] = he - hs; ++ni; }
+    }
   }
   const int stride = pw + 1;
   for (int j = warp; j < pw; j += 8) {
-    const int wlen = win_end(j, W, pw) - win_begin(j, W, pw);
+    const int wlen = EXACT ? W / pw : win_end(j, W, pw) - win_begin(j, W, pw);
     const float r0 = 1.f / (float)(ilen[0] * wlen), r1 = ni > 1 ? 1.f / (float)(ilen[1] * wlen) : 0.f;
     const float* g0 = gp + (((int64_t)b * ph + irow[0]) * pw + j) * C;
     const float* g1 = gp + (((int64_t)b * ph + irow[ni > 1 ? 1 : 0]) * pw + j) * C;
-    for (int c = lane; c < C; c += 32) G[c * stride + j] = fmaf(__ldg(g1 + c), r1, __ldg(g0 + c) * r0);
+    if (EXACT) {
+      for (int c = lane; c < C; c += 32) G[c * stride + j] = __ldg(g0 + c) * r0;
+    } else {
+      for (int c = lane; c < C; c += 32) G[c * stride + j] = fmaf(__ldg(g1 + c), r1, __ldg(g0 + c) * r0);
+    }
   }
   __syncthreads();
   const int64_t plane = (int64_t)H * W;
@@ -233,23 +241,28 @@ __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ g
       for (int e = 0; e < 4; ++e) {
         const int w = w4 * 4 + e;
         j0[e] = cell_of(w, W, pw);
-        two[e] = (j0[e] + 1 < pw) && (win_begin(j0[e] + 1, W, pw) <= w);
+        two[e] = !EXACT && (j0[e] + 1 < pw) && (win_begin(j0[e] + 1, W, pw) <= w);
       }
       float* out = base + w4 * 4;
       const float* Gc = G + warp * stride;
+#pragma unroll 4
       for (int c = warp; c < C; c += 8, Gc += 8 * stride) {
         float4 v;
-        v.x = Gc[j0[0]] + (two[0] ? Gc[j0[0] + 1] : 0.f);
-        v.y = Gc[j0[1]] + (two[1] ? Gc[j0[1] + 1] : 0.f);
-        v.z = Gc[j0[2]] + (two[2] ? Gc[j0[2] + 1] : 0.f);
-        v.w = Gc[j0[3]] + (two[3] ? Gc[j0[3] + 1] : 0.f);
+        if (EXACT) {
+          v = make_float4(Gc[j0[0]], Gc[j0[1]], Gc[j0[2]], Gc[j0[3]]);
+        } else {
+          v.x = Gc[j0[0]] + (two[0] ? Gc[j0[0] + 1] : 0.f);
+          v.y = Gc[j0[1]] + (two[1] ? Gc[j0[1] + 1] : 0.f);
+          v.z = Gc[j0[2]] + (two[2] ? Gc[j0[2] + 1] : 0.f);
+          v.w = Gc[j0[3]] + (two[3] ? Gc[j0[3] + 1] : 0.f);
+        }
         *reinterpret_cast<float4*>(out + c * plane) = v;
       }
     }
   } else {
     for (int w = lane; w < W; w += 32) {
       const int j0 = cell_of(w, W, pw);
-      const bool two = (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
+      const bool two = !EXACT && (j0 + 1 < pw) && (win_begin(j0 + 1, W, pw) <= w);
       float* out = base + w;
       const float* Gc = G + warp * stride;
       for (int c = warp; c < C; c += 8, Gc += 8 * stride) out[c * plane] = Gc[j0] + (two ? Gc[j0 + 1] : 0.f);
@@ -354,8 +367,15 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
     static const char* nch_env = getenv("SPCL_DENSE_NCH");
     int nch = SPCL_DENSE_NCH_DEFAULT;
     if (nch_env != nullptr && (nch_env[0] == '2' || nch_env[0] == '4')) nch = nch_env[0] - '0';
-    auto kern = vec4 ? (nch == 4 ? dense::pool_rows_fwd<true, 4> : dense::pool_rows_fwd<true, 2>)
-                     : (nch == 4 ? dense::pool_rows_fwd<false, 4> : dense::pool_rows_fwd<false, 2>);
+    static const char* minb_env = getenv("SPCL_DENSE_MINB");      // 6: cap registers at 42 for a sixth resident CTA
+    const bool minb6 = minb_env != nullptr && minb_env[0] == '6';
+    // default: min-blocks 1 = no register cap (76 registers, 3 CTAs / SM, every load of a batch in flight): 175 us vs
+    // 196 us for the unspecified bound, under which ptxas holds the kernel to 48 registers; SPCL_DENSE_MINB=0 restores it
+    const bool minb1 = minb_env == nullptr || minb_env[0] == '1';
+    auto kern = vec4 ? (nch == 4 ? (minb1 ? dense::pool_rows_fwd<true, 4, 1> : dense::pool_rows_fwd<true, 4, 0>)
+                                 : (minb6 ? dense::pool_rows_fwd<true, 2, 6>
+                                          : (minb1 ? dense::pool_rows_fwd<true, 2, 1> : dense::pool_rows_fwd<true, 2, 0>)))
+                     : (nch == 4 ? dense::pool_rows_fwd<false, 4, 0> : dense::pool_rows_fwd<false, 2, 0>);
     const size_t smem = sizeof(float) * ((((size_t)C * (pw + 1) + 3) & ~(size_t)3) + 8 * (size_t)nch * (size_t)W);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     if (smem > 48 * 1024)
@@ -382,7 +402,10 @@ extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points,
     const size_t smem = sizeof(float) * (size_t)C * (pw + 1);
     if (smem > 200 * 1024) return SPCL_ERR_UNSUPPORTED;
     const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0);
-    auto kern = vec4 ? dense::pool_rows_bwd<true> : dense::pool_rows_bwd<false>;
+    static const bool no_exact = getenv("SPCL_DENSE_NO_EXACT") != nullptr;     // A/B switch
+    const bool exact = !no_exact && (H % ph == 0) && (W % pw == 0);
+    auto kern = vec4 ? (exact ? dense::pool_rows_bwd<true, true> : dense::pool_rows_bwd<true, false>)
+                     : (exact ? dense::pool_rows_bwd<false, true> : dense::pool_rows_bwd<false, false>);
     if (smem > 48 * 1024)
       SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
