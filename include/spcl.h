@@ -60,6 +60,19 @@ extern "C" {
 typedef void* spcl_stream_t; /* cudaStream_t */
 
 int spcl_version(void);
+
+/* Byte sizes of the caller-owned device buffers of the tensor-core entry points below (the library never allocates).
+ * n_pad = N rounded up to SPCL_TILE, d_pad = d rounded up to 64 (<= SPCL_MAX_D).  Returns a negative error code for a
+ * bad argument.  (SURVEY.md section 8b "size_t spcl_workspace_bytes(...)".) */
+#define SPCL_WS_ZB 0         /* zb: packed bf16 operands [n_pad][d_pad] */
+#define SPCL_WS_LABELS 1     /* labels: int32 [n_pad] */
+#define SPCL_WS_SIG 2        /* sig: int32 [n_pad / 128][4] */
+#define SPCL_WS_ACC 3        /* acc: float [n_pad][4], forward scratch */
+#define SPCL_WS_ROW_STATS 4  /* row_stats: 4 planes of n_pad floats */
+#define SPCL_WS_PARTIALS 5   /* partials: float [3] (16 bytes) */
+#define SPCL_WS_SCALARS 6    /* scalars: float [4] */
+#define SPCL_WS_BWD_ZT 7     /* zt: backward scratch, bf16 [d_pad][n_pad] */
+int64_t spcl_workspace_bytes(int which, int64_t n_pad, int32_t d_pad);
 const char* spcl_error_string(int code);
 /* last CUDA error text seen by this thread inside the library (host string, never NULL) */
 const char* spcl_last_cuda_error(void);
@@ -152,12 +165,14 @@ int spcl_supcon_fwd_finish_bf16(const void* zb, int64_t n_total, int64_t n_pad, 
 
 /* ---- fused backward, tensor-core path --------------------------------------------------------
  * row_stats must hold ALL N rows (all-gathered when sharded).  dz: float [row_end-row_begin][lddz],
- * zeroed by the call; dz_i = grad_out * scale / (N tau) * sum_j T_ij z_j.  Replaces autograd of
+ * zeroed by the call; dz_i = grad_out * scale / (N tau) * sum_j T_ij z_j.  zt: caller-owned scratch of
+ * spcl_workspace_bytes(SPCL_WS_BWD_ZT, n_pad, d_pad) bytes, 128-byte aligned; the call fills it with Z^T (the
+ * layout the second GEMM reads fastest) -- its content need not survive the call.  Replaces autograd of
  * contrast_loss3.py:27,:180-197. */
 int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t d_pad, int32_t d,
                          const int32_t* labels, const int32_t* sig, const float* row_stats, const float* scalars,
                          const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
-                         int mode, float* dz, int64_t lddz, spcl_stream_t stream);
+                         int mode, float* dz, int64_t lddz, void* zt, spcl_stream_t stream);
 
 /* ---- fp32 SIMT path: same contract with fp32 operands, exact-parity mode ----------------------
  * z: float [n_total][ldz].  Exactly one of labels / tri may be non-NULL (tri needs n_half = N/2). */

@@ -41,7 +41,7 @@ SIGNATURES = {
     "spcl_supcon_fwd_finish_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,
                                     _ptr, _ptr],
     "spcl_supcon_bwd_bf16": [_ptr, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _f32, _f32,
-                             _c.c_int, _ptr, _i64, _ptr],
+                             _c.c_int, _ptr, _i64, _ptr, _ptr],
     "spcl_supcon_fwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _i64, _i64, _f32, _f32, _c.c_int, _ptr,
                             _i64, _ptr, _ptr],
     "spcl_supcon_bwd_f32": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _i64, _i64, _f32,
@@ -63,7 +63,8 @@ class ProblemF32(_c.Structure):
                 ("inv_tau", _f32), ("gamma", _f32), ("mode", _c.c_int), ("correct_grad", _c.c_int),
                 ("acc", _ptr), ("row_stats", _ptr), ("stats_stride", _i64), ("partials", _ptr), ("scalars", _ptr),
                 ("grad_out", _ptr), ("dz", _ptr), ("lddz", _i64)]
-OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error")
+OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error", "spcl_workspace_bytes")
+WS_ZB, WS_LABELS, WS_SIG, WS_ACC, WS_ROW_STATS, WS_PARTIALS, WS_SCALARS, WS_BWD_ZT = range(8)
 ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS
 
 _lib = None
@@ -102,6 +103,8 @@ def lib() -> ctypes.CDLL:
                     fn.argtypes = argtypes
                     fn.restype = _c.c_int
                 handle.spcl_version.restype = _c.c_int
+                handle.spcl_workspace_bytes.argtypes = [_c.c_int, _i64, _i32]
+                handle.spcl_workspace_bytes.restype = _i64
                 handle.spcl_error_string.argtypes = [_c.c_int]
                 handle.spcl_error_string.restype = _c.c_char_p
                 handle.spcl_last_cuda_error.restype = _c.c_char_p
@@ -120,3 +123,11 @@ def check(rc: int, what: str) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(lib(), name)(*args), name)
+
+
+def workspace_bytes(which: int, n_pad: int, d_pad: int) -> int:
+    """``spcl_workspace_bytes``: size of a caller-owned buffer of the tensor-core entry points."""
+    n = int(lib().spcl_workspace_bytes(which, n_pad, d_pad))
+    if n < 0:
+        check(n, "spcl_workspace_bytes")
+    return n

@@ -523,7 +523,24 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const float* __restrict__ 
 
 using namespace spcl;
 
-extern "C" int spcl_version(void) { return 101; }
+extern "C" int spcl_version(void) { return 200; }
+
+// Sizes of the caller-owned device buffers of the tensor-core path (the library never allocates), so a binding in
+// any language can size them without reading DESIGN.md.  n_pad = N rounded up to SPCL_TILE, d_pad = d rounded up to 64.
+extern "C" int64_t spcl_workspace_bytes(int which, int64_t n_pad, int32_t d_pad) {
+  if (n_pad <= 0 || n_pad % SPCL_TILE != 0 || d_pad <= 0 || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_INVALID_ARG;
+  switch (which) {
+    case SPCL_WS_ZB: return n_pad * d_pad * 2;                 // packed bf16 operands [n_pad][d_pad]
+    case SPCL_WS_LABELS: return n_pad * 4;                     // int32 label codes
+    case SPCL_WS_SIG: return n_pad / SPCL_TILE * 16;           // per-128-anchor label signature
+    case SPCL_WS_ACC: return n_pad * 16;                       // forward scratch, float4 per anchor
+    case SPCL_WS_ROW_STATS: return n_pad * 16;                 // 4 planes of n_pad floats
+    case SPCL_WS_PARTIALS: return 16;                          // 3 floats (+ pad)
+    case SPCL_WS_SCALARS: return 16;                           // loss, ratio, scale, scale / N
+    case SPCL_WS_BWD_ZT: return n_pad * d_pad * 2;             // backward scratch: Z^T bf16 [d_pad][n_pad]
+    default: return SPCL_ERR_INVALID_ARG;
+  }
+}
 
 extern "C" const char* spcl_error_string(int code) {
   switch (code) {

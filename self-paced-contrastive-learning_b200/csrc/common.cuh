@@ -40,6 +40,11 @@ __device__ __forceinline__ float sp_weight(float l, float gamma, float inv_gamma
   return 1.f;
 }
 
+// 1 / gamma for the soft rule.  gamma == 0 is legal in the reference (PScheduler's default begin_value, infonce.py:34-53):
+// 1 - l / 0 = -inf for every l > 0, so every positive weight is 0 and the loss is 0; FLT_MAX gives the same weights
+// without producing inf * 0.
+inline float inv_gamma_of(float gamma) { return gamma > 0.f ? 1.f / gamma : 3.402823466e+38f; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -282,6 +282,12 @@ __global__ void __launch_bounds__(256) pool_points_fwd(const float* __restrict__
   if (r >= rows) return;
   const int64_t b = r / P;
   const int q = pts[r];
+  if (static_cast<unsigned>(q) >= static_cast<unsigned>(ph * pw)) {
+    // device-resident coordinates cannot be range-checked on the host without a sync: fail like torch's indexing
+    // kernels do (device-side assert) instead of reading / atomically writing out of bounds
+    if (lane == 0) printf("spcl: point coordinate %d outside the %d x %d pooled grid (row %lld)\n", q, ph, pw, (long long)r);
+    __trap();
+  }
   const int i = q / pw, j = q % pw;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph), ws = win_begin(j, W, pw), we = win_end(j, W, pw);
   const float inv_area = 1.f / (float)((he - hs) * (we - ws));
@@ -311,6 +317,12 @@ __global__ void __launch_bounds__(256) pool_points_bwd(const float* __restrict__
   if (r >= rows) return;
   const int64_t b = r / P;
   const int q = pts[r];
+  if (static_cast<unsigned>(q) >= static_cast<unsigned>(ph * pw)) {
+    // device-resident coordinates cannot be range-checked on the host without a sync: fail like torch's indexing
+    // kernels do (device-side assert) instead of reading / atomically writing out of bounds
+    if (lane == 0) printf("spcl: point coordinate %d outside the %d x %d pooled grid (row %lld)\n", q, ph, pw, (long long)r);
+    __trap();
+  }
   const int i = q / pw, j = q % pw;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph), ws = win_begin(j, W, pw), we = win_end(j, W, pw);
   const float inv_area = 1.f / (float)((he - hs) * (we - ws));

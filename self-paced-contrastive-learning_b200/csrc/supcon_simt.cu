@@ -663,7 +663,7 @@ static int check_common(const float* z, int64_t n_total, int32_t d, int64_t ldz,
   if (tri != nullptr && n_half * 2 != n_total) return SPCL_ERR_INVALID_ARG;
   if (row_begin < 0 || row_end > n_total || row_begin >= row_end) return SPCL_ERR_INVALID_ARG;
   if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_EXCL) return SPCL_ERR_INVALID_ARG;
-  if ((mode == SPCL_MODE_HARD || mode == SPCL_MODE_SOFT) && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
+  if ((mode == SPCL_MODE_HARD || mode == SPCL_MODE_SOFT) && !(gamma >= 0.f)) return SPCL_ERR_INVALID_ARG;
   return SPCL_OK;
 }
 
@@ -679,7 +679,7 @@ extern "C" int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, i
   int rc = simt::check_common(z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
   if (row_stats == nullptr || partials == nullptr || stats_stride < n_total) return SPCL_ERR_INVALID_ARG;
-  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, inv_gamma_of(gamma), mode};
   const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
   simt::fwd_kernel<<<grid, simt::NT, 0, static_cast<cudaStream_t>(stream)>>>(
       a, row_stats, stats_stride, partials);
@@ -697,7 +697,7 @@ extern "C" int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, i
   if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d ||
       stats_stride < n_total)
     return SPCL_ERR_INVALID_ARG;
-  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  simt::Args a{z, n_total, d, ldz, labels, tri, n_half, row_begin, row_end, inv_tau, gamma, inv_gamma_of(gamma), mode};
   const unsigned grid = static_cast<unsigned>(ceil_div(row_end - row_begin, simt::BM));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d <= 64) simt::bwd_kernel<4><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
@@ -728,7 +728,7 @@ extern "C" int spcl_supcon_fwd_f32_split(const float* z, int64_t n_total, int32_
   if (acc == nullptr || row_stats == nullptr || partials == nullptr || stats_stride < n_total ||
       (reinterpret_cast<uintptr_t>(acc) & 15))
     return SPCL_ERR_INVALID_ARG;
-  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, inv_gamma_of(gamma), mode};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t rows = row_end - row_begin;
   unsigned gy = 1;
@@ -759,7 +759,7 @@ extern "C" int spcl_supcon_bwd_f32_split(const float* z, int64_t n_total, int32_
   if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d ||
       stats_stride < n_total)
     return SPCL_ERR_INVALID_ARG;
-  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, 1.f / gamma, mode};
+  simt::Args a{z, n_total, d, ldz, labels, nullptr, 0, row_begin, row_end, inv_tau, gamma, inv_gamma_of(gamma), mode};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t rows = row_end - row_begin;
   unsigned gy = 1;
@@ -790,7 +790,7 @@ static int fill_group(const spcl_problem_f32* pr, int count, bool bwd, simt::Gro
       return SPCL_ERR_INVALID_ARG;
     if (bwd && (q.grad_out == nullptr || q.dz == nullptr || q.lddz < q.d)) return SPCL_ERR_INVALID_ARG;
     g.p[k] = simt::Args{q.z, q.n_total, q.d, q.ldz, q.labels, nullptr, 0, 0, q.n_total, q.inv_tau, q.gamma,
-                        1.f / q.gamma, q.mode};
+                        inv_gamma_of(q.gamma), q.mode};
     g.sp[k] = simt::pick_split(q.n_total, q.n_total, g.gy[k]);
     g.gx[k] = static_cast<unsigned>(ceil_div(q.n_total, static_cast<int64_t>(simt::BM)));
     g.acc[k] = reinterpret_cast<float4*>(q.acc);

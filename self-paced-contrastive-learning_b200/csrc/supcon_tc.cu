@@ -63,6 +63,12 @@ constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp =
 #ifndef SPCL_BWD_POLY_PAIRS
 #define SPCL_BWD_POLY_PAIRS 3
 #endif
+// The backward's T.Z GEMM of a tile is issued in this many K-parts (1, 2 or 4), each as soon as the epilogue has
+// written its share of T: the S/T buffer's lifetime (S issue -> epilogue -> T.Z done) bounds the kernel at
+// lifetime / 3 per tile, and with one part the whole T.Z (+ its barrier hand-off) sits at the end of that chain.
+#ifndef SPCL_BWD_TZ_PARTS
+#define SPCL_BWD_TZ_PARTS 1
+#endif
 
 struct Params {
   int64_t N, n_pad;
@@ -118,7 +124,7 @@ struct Barriers {
   uint64_t empty[kMaxSlots];
   uint64_t s_full[kMaxBufs];
   uint64_t s_empty[kMaxBufs];
-  uint64_t t_full[kMaxBufs];
+  uint64_t t_full[kMaxBufs][4];
   uint64_t a_full, a_empty, dz_full, dz_empty;
   uint32_t tmem_base;
 };
@@ -304,7 +310,7 @@ __device__ __forceinline__ void init_barriers(Barriers* b, int slot_consumers, i
   for (int i = 0; i < kMaxBufs; ++i) {
     mbar_init(&b->s_full[i], 1);
     mbar_init(&b->s_empty[i], sbuf_consumers);
-    mbar_init(&b->t_full[i], 4);
+    for (int j = 0; j < 4; ++j) mbar_init(&b->t_full[i][j], 4);
   }
   mbar_init(&b->a_full, 1);
   mbar_init(&b->a_empty, a_consumers);
@@ -532,6 +538,92 @@ __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&v)[32], const fl
     pk[(e >> 1) + 0] = pack_bf16x2(t0, t1);
     pk[(e >> 1) + 1] = pack_bf16x2(t2, t3);
   }
+}
+
+// Software-pipelined form of bwd_chunk_fast.  ncu's SASS view of the straight-line version showed ptxas grouping the
+// chunk by instruction kind -- all argument FFMA2s, then the 26 MUFU.EX2 back to back (each paced ~8-12 cycles behind
+// the previous one: half of the chunk's time), then the FADD2 / FMUL2 / F2FP tail -- so the quarter-rate MUFU pipe and
+// the FMA pipe took turns instead of overlapping.  Here every statement is a volatile asm in the order it should issue:
+// pair p's two exponentials are separated by the (u_i + u_j) add, the multiply and the bf16 pack of pair p - 2 and by
+// the argument FFMA2 of pair p + 1, and the polynomial (FMA-pipe) pairs are spread between the MUFU pairs.
+#ifndef SPCL_BWD_SWP
+#define SPCL_BWD_SWP 1
+#endif
+__device__ __forceinline__ uint64_t v_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t v_add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t v_mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float v_ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t v_cvt_bf16x2(uint64_t t) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.bf16x2.f32 %0, hi, lo;\n\t}" : "=r"(r) : "l"(t));
+  return r;
+}
+__device__ __forceinline__ void lds_v4(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+
+__device__ __forceinline__ void bwd_chunk_fast_swp(const uint32_t (&v)[32], uint32_t u_addr, const ExpK& k, uint64_t uiui,
+                                                   uint32_t (&pk)[16]) {
+  uint64_t uj[16], arg[16], ex[16];
+  float alo[16] = {}, ahi[16] = {}, elo[16] = {}, ehi[16] = {};    // (poly pairs never touch theirs)
+  // column statistics u_j of the chunk: 8 x LDS.128 (shared window, not generic loads)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float a, b, c, d;
+    lds_v4(u_addr + q * 16, a, b, c, d);
+    uj[2 * q] = pack_f32x2(a, b);
+    uj[2 * q + 1] = pack_f32x2(c, d);
+  }
+  auto stage_a = [&](int p) {          // exponent argument (MUFU pairs) or the whole FMA-pipe exponential (poly pairs)
+    const uint64_t d2 = pack_u32x2(v[2 * p], v[2 * p + 1]);
+    if (use_poly(p, SPCL_BWD_POLY_PAIRS)) {
+      const uint64_t t = v_fma2(d2, k.c2, k.mg);
+      const uint64_t nn = v_fma2(t, k.neg1, k.mg);
+      const uint64_t f = v_fma2(d2, k.c2, nn);
+      uint64_t q = v_fma2(f, k.c[3], k.c[2]);
+      q = v_fma2(q, f, k.c[1]);
+      q = v_fma2(q, f, k.c[0]);
+      const uint32_t q0 = static_cast<uint32_t>(q), q1 = static_cast<uint32_t>(q >> 32);
+      const uint32_t t0 = static_cast<uint32_t>(t), t1 = static_cast<uint32_t>(t >> 32);
+      ex[p] = pack_u32x2(q0 + (t0 << 23), q1 + (t1 << 23));
+    } else {
+      arg[p] = v_fma2(d2, k.c2, k.nc2);
+      unpack_f32x2(arg[p], alo[p], ahi[p]);
+    }
+  };
+  auto stage_c = [&](int p) {          // T = E (u_i + u_j) -> bf16x2
+    if (!use_poly(p, SPCL_BWD_POLY_PAIRS)) ex[p] = pack_f32x2(elo[p], ehi[p]);
+    pk[p] = v_cvt_bf16x2(v_mul2(ex[p], uj[p]));
+  };
+  stage_a(0);
+  stage_a(1);
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const bool mufu = !use_poly(p, SPCL_BWD_POLY_PAIRS);
+    if (mufu) elo[p] = v_ex2(alo[p]);
+    uj[p] = v_add2(uj[p], uiui);
+    if (p + 2 < 16) stage_a(p + 2);
+    if (mufu) ehi[p] = v_ex2(ahi[p]);
+    if (p >= 2) stage_c(p - 2);
+  }
+  stage_c(14);
+  stage_c(15);
 }
 
 template <int MODE>
@@ -1015,7 +1107,15 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restr
 // =================================================================================================
 // backward
 // =================================================================================================
-__global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
+// Operand layouts of the backward (measured tcgen05.mma rates, tools/mma_bench.cu, cycles per K = 16 step of a
+// 128 x 128 product: A from TMEM + K-major B 69, SS 98-137 whatever the B layout, A from TMEM + MN-major B 90-125;
+// the shared-memory-bound shapes vary from box to box, the TMEM + K-major one does not):
+//   column tiles are staged from Z^T (bf16 [d_pad][n_pad], written by transpose_kernel): a slot = 2 panels of
+//   d_pad rows x 64 anchors.  T.Z reads it K-major (K = anchors), the S product reads the same bytes MN-major
+//   (N = anchors) -- S is an SS product and A-operand bound either way, so the fast layout goes to T.Z.
+//   The row block's own A tile still comes from Z (K-major).
+__global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                          const __grid_constant__ CUtensorMap tmap_t, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const SmemView sm = carve(smem_raw, p, TILE, true);
   Barriers* bar = sm.bar;
@@ -1023,13 +1123,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
 
   if (warp == kMmaWarp0 && lane == 0) init_barriers(bar, /*slot released by the T.Z commit*/ 1, 1, /*a_empty*/ 1);
   if (warp == kAllocWarp) tmem_alloc<kTmemCols>(&bar->tmem_base);
-  if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tmap);
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tensormap(&tmap);
+    prefetch_tensormap(&tmap_t);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bar->tmem_base;
   const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
   const uint32_t sbuf0 = static_cast<uint32_t>(p.d_pad);       // TMEM columns [0, d_pad) hold dZ
+  const uint32_t panel_t = static_cast<uint32_t>(p.d_pad) * 128u;   // one Z^T panel: d_pad rows x 64 anchors
 
   int64_t f0, f1;
   cta_range(p, f0, f1);
@@ -1051,8 +1155,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
         TRACE(0, c.it, 0);
         mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
         uint8_t* dst = sm.slot(slot);
-        for (int k = 0; k < p.dc; ++k)
-          tma_load_2d(dst + k * CHUNK_BYTES, &tmap, &bar->full[slot], k * 64, static_cast<int32_t>(c.t * TILE));
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(dst + h * panel_t, &tmap_t, &bar->full[slot], static_cast<int32_t>(c.t * TILE + h * 64), 0);
         bulk_load_1d(sm.slot_labels(slot), p.labels + static_cast<int64_t>(c.t) * TILE, META_LABEL_BYTES, &bar->full[slot]);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -1084,7 +1188,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
       TRACE(1, c.it, 0);
       tc_fence_after();
       if (elect_one()) {
-        issue_s_mma<TILE>(tmem_u + sbuf0 + sb.idx * TILE, a_base, smem_u32(sm.slot(ss.idx)), 0, nk);
+        // S = Z_I (K-major A) x Z^T slot read MN-major: the 64-anchor MN atoms are the two panels (LBO = panel
+        // bytes), 8-row K (= d) groups are 1024 B apart (SBO); each K = 16 step advances 16 rows.
+        constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, false, true);
+        const uint32_t d_tmem = tmem_u + sbuf0 + sb.idx * TILE;
+        const uint32_t b_base = smem_u32(sm.slot(ss.idx));
+        const int nk_s = (p.dbg & 2048) ? 1 : nk;             // timing experiment: one K step only (results wrong)
+        for (int kk = 0; kk < nk_s; ++kk) {
+          const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
+          mma_ss(d_tmem, make_smem_desc_sw128(a_base + pa, 16, 1024),
+                 make_smem_desc_sw128(b_base + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024), idesc_s,
+                 kk != 0 ? 1u : 0u);
+        }
         tc_commit(&bar->s_full[sb.idx]);
         if (c.last()) tc_commit(&bar->a_empty);               // only the S MMAs read the A tile
       }
@@ -1094,35 +1209,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
     }
   } else if (warp == kMmaWarp1) {
     // ---- T.Z issuer
-    const uint32_t idesc_tz = make_idesc_bf16(TILE, p.d_pad, false, true);
+    const uint32_t idesc_tz = make_idesc_bf16(TILE, p.d_pad, false, false);
     const bool safe = (p.dbg & 8) != 0;
     const uint32_t nb = static_cast<uint32_t>(p.nbuf);
     Ring ts(p.nslot), tb(p.nbuf);
     for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ts.next(), tb.next()) {
       const bool first = c.first();
-      if (lane == 0) {
-        mbar_wait(&bar->t_full[tb.idx], tb.ph);
-        if (first) mbar_wait(&bar->dz_empty, (c.seg & 1) ^ 1);
-      }
-      __syncwarp();
-      if (c.it + nb - 1 < c.n) named_bar_sync(2, 64);         // S(it + nbuf - 1) has been issued
-      TRACE(1, c.it, 2);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t b_base = smem_u32(sm.slot(ts.idx));
-        const uint32_t a_tmem = tmem_u + sbuf0 + tb.idx * TILE;
+      const uint32_t b_base = smem_u32(sm.slot(ts.idx));
+      const uint32_t a_tmem = tmem_u + sbuf0 + tb.idx * TILE;
+      constexpr int kParts = SPCL_BWD_TZ_PARTS, kPerPart = (TILE / 16) / kParts;
 #pragma unroll
-        for (int k = 0; k < TILE / 16; ++k) {
-          // B = Z_J read MN-major: the 64-wide MN (= d) atoms are the TMA panels (LBO = panel bytes),
-          // 8-row K (= j) groups are 1024 B apart (SBO); each K = 16 step advances 16 rows.
-          const uint64_t bd = make_smem_desc_sw128(b_base + k * 16 * 128, CHUNK_BYTES, 1024);
-          mma_ts(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && k == 0) ? 0u : 1u);
+      for (int part = 0; part < kParts; ++part) {
+        if (lane == 0) {
+          mbar_wait(&bar->t_full[tb.idx][part], tb.ph);       // T columns of this K-part written
+          if (first && part == 0) mbar_wait(&bar->dz_empty, (c.seg & 1) ^ 1);
         }
-        tc_commit(&bar->empty[ts.idx]);
-        if (safe) tc_commit(&bar->s_empty[tb.idx]);
-        if (c.last()) tc_commit(&bar->dz_full);
+        __syncwarp();
+        if (part == 0) {
+          if (c.it + nb - 1 < c.n) named_bar_sync(2, 64);     // S(it + nbuf - 1) has been issued
+          TRACE(1, c.it, 2);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = part * kPerPart; k < (part + 1) * kPerPart; ++k) {
+            if ((p.dbg & 4096) && k != 0) continue;           // timing experiment: one K step only (results wrong)
+            // B = Z^T slot read K-major: N = d rows (8-row groups 1024 B apart), K = anchors: step k lives in
+            // panel k / 4 at byte offset (k % 4) * 32 of the 128-byte swizzle row.
+            const uint64_t bd = make_smem_desc_sw128(b_base + static_cast<uint32_t>(k >> 2) * panel_t +
+                                                     static_cast<uint32_t>(k & 3) * 32u, 16, 1024);
+            mma_ts(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && k == 0) ? 0u : 1u);
+          }
+          if (part == kParts - 1) {
+            tc_commit(&bar->empty[ts.idx]);
+            if (safe) tc_commit(&bar->s_empty[tb.idx]);
+            if (c.last()) tc_commit(&bar->dz_full);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
       if (c.it + nb < c.n) named_bar_arrive(1, 64);           // S(it + nbuf) may go
       TRACE(1, c.it, 3);
     }
@@ -1198,8 +1323,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
           if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
           uint32_t pk[16];
-          if (!slow) {
+          if (p.dbg & 1) {                                     // timing experiment: no epilogue math (results wrong)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = cur[2 * e] ^ cur[2 * e + 1];
+          } else if (!slow) {
+#if SPCL_BWD_SWP
+            bwd_chunk_fast_swp(cur, smem_u32(u_s + ch * 32), ek, uiui, pk);
+#else
             bwd_chunk_fast(cur, u_s + ch * 32, ek, uiui, pk);
+#endif
           } else if (p.mode == SPCL_MODE_SOFT) {
             bwd_chunk_slow<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
                                            u_i, pk);
@@ -1213,11 +1345,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           if (ch < 3) tmem_wait_ld();
           // T (bf16) overwrites S columns [16 ch, 16 ch + 16), all of which were loaded before
           tmem_st_32x32b_x16(taddr + ch * 16, pk);
+          constexpr int kChPerPart = 4 / SPCL_BWD_TZ_PARTS;
+          if ((ch + 1) % kChPerPart == 0) {                   // this K-part of T is complete: its T.Z may be issued
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar->t_full[buf][(ch + 1) / kChPerPart - 1]);
+          }
         }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->t_full[buf]);
         TRACE(2 + warp, c.it, 1);
       }
 
@@ -1251,6 +1386,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
   if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// Z [n_pad][d_pad] bf16 -> Z^T [d_pad][n_pad] bf16 (64 x 64 tiles through shared memory, 128-byte rows both ways).
+// 2 x n_pad x d_pad x 2 bytes of HBM traffic: 16 MB at cfg3 (~5 us), once per backward.
+__global__ void __launch_bounds__(256) transpose_kernel(const uint16_t* __restrict__ z, uint16_t* __restrict__ zt,
+                                                        int64_t n_pad, int d_pad) {
+  __shared__ uint16_t tile[64][66];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads, 2 elements per thread per row
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + 8 * i;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(z + (r0 + r) * d_pad + c0 + 2 * tx);
+    tile[r][2 * tx] = static_cast<uint16_t>(v);
+    tile[r][2 * tx + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ty + 8 * i;
+    const uint32_t v = static_cast<uint32_t>(tile[2 * tx][c]) | (static_cast<uint32_t>(tile[2 * tx + 1][c]) << 16);
+    *reinterpret_cast<uint32_t*>(zt + static_cast<int64_t>(c0 + c) * n_pad + r0 + 2 * tx) = v;
   }
 }
 
@@ -1598,14 +1757,36 @@ static int make_zb_tensor_map(CUtensorMap* map, const void* zb, int64_t n_pad, i
   return SPCL_OK;
 }
 
-static int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
+// Z^T [d_pad][n_pad]: box = 64 anchors (one 128-byte swizzle row) x d_pad rows
+static int make_zt_tensor_map(CUtensorMap* map, const void* zt, int64_t n_pad, int d_pad) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return SPCL_ERR_NO_DRIVER;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(n_pad), static_cast<cuuint64_t>(d_pad)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(n_pad) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(d_pad)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(zt), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(Z^T)");
+    return SPCL_ERR_CUDA;
   }
-  return sms;
+  return SPCL_OK;
+}
+
+static int num_sms() {
+  constexpr int kMaxDev = 64;
+  static int sms[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
 }
 
 static int pick_slots(int dc, int bn, bool meta) {
@@ -1667,7 +1848,7 @@ static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad,
   if (!(inv_tau > 0.f) || mode < SPCL_MODE_NONE || mode > SPCL_MODE_SOFT) return SPCL_ERR_INVALID_ARG;
   // exp(S - 1/tau) must stay a normal fp32 for S >= -1/tau
   if (inv_tau > 40.f) return SPCL_ERR_UNSUPPORTED;   // also keeps the exponent splice of ex2_poly2 in range
-  if (mode != SPCL_MODE_NONE && !(gamma > 0.f)) return SPCL_ERR_INVALID_ARG;
+  if (mode != SPCL_MODE_NONE && !(gamma >= 0.f)) return SPCL_ERR_INVALID_ARG;
   p.N = n_total;
   p.n_pad = n_pad;
   p.row_begin = row_begin;
@@ -1681,7 +1862,7 @@ static int fill_params(Params& p, int64_t n_total, int64_t n_pad, int32_t d_pad,
   p.sig = reinterpret_cast<const int4*>(sig);
   p.inv_tau = inv_tau;
   p.gamma = gamma;
-  p.inv_gamma = gamma > 0.f ? 1.f / gamma : 0.f;
+  p.inv_gamma = inv_gamma_of(gamma);
   p.mode = mode;
   p.c2 = inv_tau * kLog2e;
   const float ci = floorf(p.c2);
@@ -1875,11 +2056,12 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
                                     const int32_t* labels, const int32_t* sig, const float* row_stats,
                                     const float* scalars, const float* grad_out, int64_t row_begin,
                                     int64_t row_end, float inv_tau, float gamma, int mode, float* dz,
-                                    int64_t lddz, spcl_stream_t stream) {
+                                    int64_t lddz, void* zt, spcl_stream_t stream) {
   tc::Params p{};
   int rc = tc::fill_params(p, n_total, n_pad, d_pad, labels, sig, row_begin, row_end, inv_tau, gamma, mode);
   if (rc != SPCL_OK) return rc;
-  if (zb == nullptr || row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr)
+  if (zb == nullptr || row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr ||
+      zt == nullptr || (reinterpret_cast<uintptr_t>(zt) & 127))
     return SPCL_ERR_INVALID_ARG;
   if (d <= 0 || d > d_pad || lddz < d) return SPCL_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(zb) & 15) || (reinterpret_cast<uintptr_t>(labels) & 15) ||
@@ -1923,8 +2105,14 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
   const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot, 128, true) + 1024;
   rc = tc::set_smem(tc::bwd_kernel, smem);
   if (rc != SPCL_OK) return rc;
+  CUtensorMap tmap_t;
+  rc = tc::make_zt_tensor_map(&tmap_t, zt, n_pad, d_pad);
+  if (rc != SPCL_OK) return rc;
+  tc::transpose_kernel<<<dim3(static_cast<unsigned>(n_pad / 64), static_cast<unsigned>(d_pad / 64)), 256, 0, s>>>(
+      static_cast<const uint16_t*>(zb), static_cast<uint16_t*>(zt), n_pad, d_pad);
+  SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16/transpose");
   SPCL_CUDA_TRY(cudaMemsetAsync(dz, 0, static_cast<size_t>(row_end - row_begin) * lddz * sizeof(float), s));
-  tc::bwd_kernel<<<tc::grid_for(p), tc::NTHREADS, smem, s>>>(tmap, p);
+  tc::bwd_kernel<<<tc::grid_for(p), tc::NTHREADS, smem, s>>>(tmap, tmap_t, p);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16");
   return SPCL_OK;
 }

@@ -101,9 +101,10 @@ class NativeBackend:
                       mode, d):
         N, d_pad = z_all.shape
         dz = torch.empty(plan.rows_loc, d, dtype=torch.float32, device=z_all.device)
+        zt = torch.empty(nat.workspace_bytes(nat.WS_BWD_ZT, N, d_pad), dtype=torch.uint8, device=z_all.device)
         nat.call("spcl_supcon_bwd_bf16", _ptr(z_all), N, N, d_pad, d, _ptr(labels_all), _ptr(sig),
                  _ptr(row_stats_all), _ptr(scalars), _ptr(grad), plan.row_begin, plan.row_end, inv_tau, gamma, mode,
-                 _ptr(dz), dz.stride(0), _stream(z_all))
+                 _ptr(dz), dz.stride(0), _ptr(zt), _stream(z_all))
         return dz
 
 

@@ -26,6 +26,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 from torch import Tensor, nn
 
+from . import ops
 from .dense import DenseProjectionTail, point_coordinates
 from .losses import SelfPacedSupConLoss, SupConLoss1
 from .projectors import Normalize
@@ -106,11 +107,13 @@ class LabelCache:
 
     def __call__(self, labels, device) -> Tensor:
         if isinstance(labels, Tensor):
-            return labels.to(device=device, dtype=torch.int32)
+            # same equality classes as torch.eq on the tensor itself (floats are not truncated, wide int64 values
+            # do not wrap): ops.label_codes
+            return ops.label_codes(labels, labels.shape[0], device)
         key = (str(device), tuple(int(v) for v in labels))
         hit = self._store.get(key)
         if hit is None:
-            hit = torch.tensor(key[1], dtype=torch.int32).to(device, non_blocking=True)
+            hit = ops.label_codes(list(key[1]), len(key[1]), device)
             self._store[key] = hit
             if len(self._store) > self._cap:
                 self._store.popitem(last=False)

@@ -13,8 +13,11 @@ Extra keyword arguments (accepted through the reference's ``**kwargs``):
 
 ``precision``   "auto" (default) | "bf16" | "fp32".  bf16 = tcgen05 tensor-core kernels, fp32 = SIMT
                 kernels that match the reference to fp32 rounding.  "auto" takes fp32 for the
-                tri-state ``mask=`` form and for N < 1024 (the reference's own batch sizes), bf16
-                above.
+                tri-state ``mask=`` form, for N < 1024 (the reference's own batch sizes) and for
+                temperatures below 0.025 (which the tensor-core kernels reject), bf16 above.  Note for
+                ``weight_update="hard"``: with bf16 operands a pair whose l_ij lies within operand rounding
+                (~2**-8 / T) of gamma can land on the other side of the threshold than in the fp32
+                reference; ask for ``precision="fp32"`` when that must not happen.
 ``check_nan``   True (default) raises ``RuntimeError`` on a NaN loss right away like the reference
                 (:203-204), which costs one host sync per call; False leaves the check to the caller.
 ``validate``    True (default) keeps the reference's ``assert is_normalized`` (:154), active only
@@ -44,7 +47,14 @@ def is_normalized(feature: Tensor, dim: int = 1) -> bool:
     return bool(torch.allclose(norms, torch.ones_like(norms)))
 
 
-def _pick_tc(precision: str, N: int, has_tri: bool, mode: int = nat.MODE_NONE) -> bool:
+#: the tensor-core kernels keep exp(S - 1/T) a normal fp32 only for 1/T <= 40 (supcon_tc.cu fill_params)
+_TC_MAX_INV_TAU = 40.0
+
+
+def _pick_tc(precision: str, N: int, has_tri: bool, mode: int = nat.MODE_NONE, temperature: float = 0.07) -> bool:
+    """True = tcgen05 bf16 kernels, False = fp32 SIMT kernels.  ``"auto"`` never picks a path that would reject the
+    call: tri-state masks, ``exclude_other_pos`` and temperatures below 0.025 stay on the fp32 kernels, which carry
+    them at any N (the reference computes a loss for all of them)."""
     if mode == nat.MODE_EXCL:
         # exclude_other_pos (:97-100) has a per-pair denominator; it is carried by the fp32 kernels only
         if precision == "bf16":
@@ -56,7 +66,7 @@ def _pick_tc(precision: str, N: int, has_tri: bool, mode: int = nat.MODE_NONE) -
         return False
     if precision != "auto":
         raise ValueError(f"precision must be 'auto', 'bf16' or 'fp32', got {precision!r}")
-    return (not has_tri) and N >= _AUTO_TC_MIN_N
+    return (not has_tri) and N >= _AUTO_TC_MIN_N and 1.0 / float(temperature) <= _TC_MAX_INV_TAU
 
 
 class _Diagnostics:
@@ -173,7 +183,7 @@ def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Op
         labels = ops.label_codes(target, n, dev)
     else:                                     # :140-143  SimCLR
         labels = torch.arange(n, dtype=torch.int32, device=dev)
-    use_tc = _pick_tc(precision, 2 * n, tri is not None, int(mode))
+    use_tc = _pick_tc(precision, 2 * n, tri is not None, int(mode), temperature)
     if graph_cache is not None and tri is None and int(mode) != nat.MODE_EXCL and not torch.compiler.is_compiling():
         key = (n, z1.shape[1], str(dev), float(temperature), float(gamma), int(mode), bool(correct_grad), use_tc)
         runner = graph_cache.get(key)
@@ -236,7 +246,7 @@ class _FusedSupConBase(nn.Module):
         outer, d = feat1.shape[0], feat1.shape[1]
         n = feat1.numel() // d
         gamma, mode, cg = self._gamma_mode_cg()
-        if not _pick_tc(self._precision, 2 * n, False, int(mode)):
+        if not _pick_tc(self._precision, 2 * n, False, int(mode), self._t):
             def rows(x):
                 y = ops.l2norm_fwd(x.float(), 1, eps)[0]
                 return y.reshape(outer, d, -1).permute(0, 2, 1).reshape(n, d)
@@ -348,7 +358,7 @@ def grouped_forward(criteria, feats, targets=None, cuda_graph: bool = False):
             assert is_normalized(z1) and is_normalized(z2), "features need to be normalized first"
         gamma, mode, cg = crit._gamma_mode_cg()
         n = z1.shape[0]
-        if int(mode) == nat.MODE_EXCL or _pick_tc(crit._precision, 2 * n, False, int(mode)):
+        if int(mode) == nat.MODE_EXCL or _pick_tc(crit._precision, 2 * n, False, int(mode), crit._t):
             groupable = False
         metas.append((crit._t, gamma, mode, cg))
     if not groupable:

@@ -9,6 +9,7 @@ plumbing only; all arithmetic on the path happens in ``libspcl_b200.so``.
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
 import os
 from typing import Optional, Tuple
@@ -31,6 +32,24 @@ def _stream(t: Tensor):
 
 def pad_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def on_device_of(idx: int):
+    """Runs the wrapped op with the CUDA device of its ``idx``-th positional tensor current.
+
+    The C ABI launches kernels, memsets, ``cudaFuncSetAttribute`` and tensor-map encodes on the CURRENT device;
+    tensors that live on another GPU of the process (``model.to('cuda:1')`` without ``set_device``, one module per
+    device) would otherwise hit an invalid-resource-handle error where the reference (pure torch) just works."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            t = args[idx]
+            if not (isinstance(t, Tensor) and t.is_cuda) or t.device.index == torch.cuda.current_device():
+                return fn(*args, **kwargs)
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return wrapped
+    return deco
 
 
 def _require_cuda(*ts: Tensor) -> None:
@@ -69,7 +88,11 @@ def label_codes(target, n: int, device) -> Tensor:
     t = target.to(device)
     if t.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8, torch.bool):
         return t.to(torch.int32)
-    # int64 / floating labels: exact equality classes (this path synchronises; pass int32 to avoid it)
+    if t.dtype == torch.int64 and (t.numel() == 0 or int(t.abs().max()) < 2 ** 31 - 1):
+        # torch's default label dtype: a plain cast keeps the equality classes (one scalar read, no sort);
+        # pass int32 labels to avoid even that synchronisation
+        return t.to(torch.int32)
+    # wide int64 / floating labels: exact equality classes through a sort (this path synchronises)
     _, inv = torch.unique(t, return_inverse=True)
     return inv.to(torch.int32)
 
@@ -96,6 +119,7 @@ def _f32_split(has_labels: bool, mode: int) -> bool:
 
 
 @torch.library.custom_op("spcl::supcon_fwd", mutates_args=(), device_types="cuda")
+@on_device_of(0)
 def supcon_fwd(z1: Tensor, z2: Tensor, labels: Optional[Tensor], tri: Optional[Tensor], temperature: float,
                gamma: float, mode: int, correct_grad: bool, use_tc: bool
                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
@@ -179,6 +203,7 @@ def _(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc):
 
 
 @torch.library.custom_op("spcl::supcon_bwd", mutates_args=(), device_types="cuda")
+@on_device_of(1)
 def supcon_bwd(grad_loss: Tensor, zpack: Tensor, labels_full: Tensor, sig: Tensor, tri: Optional[Tensor],
                row_stats: Tensor, scalars: Tensor, temperature: float, gamma: float, mode: int, use_tc: bool,
                n: int, d: int) -> Tensor:
@@ -192,9 +217,10 @@ def supcon_bwd(grad_loss: Tensor, zpack: Tensor, labels_full: Tensor, sig: Tenso
     dz = torch.empty(N, d, dtype=torch.float32, device=dev)
     if use_tc:
         n_pad, d_pad = zpack.shape
+        zt = torch.empty(nat.workspace_bytes(nat.WS_BWD_ZT, n_pad, d_pad), dtype=torch.uint8, device=dev)
         nat.call("spcl_supcon_bwd_bf16", _ptr(zpack), N, n_pad, d_pad, d, _ptr(labels_full), _ptr(sig),
                  _ptr(row_stats), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz),
-                 dz.stride(0), st)
+                 dz.stride(0), _ptr(zt), st)
     elif _f32_split(tri is None, mode):
         nat.call("spcl_supcon_bwd_f32_split", _ptr(zpack), N, d, zpack.stride(0), _ptr(labels_full), _ptr(row_stats),
                  row_stats.stride(0), _ptr(scalars), _ptr(g), 0, N, inv_tau, float(gamma), int(mode), _ptr(dz),
@@ -276,6 +302,7 @@ class _RawSupCon(torch.autograd.Function):
     (``spcl_supcon_raw_bwd``).  Tensor-core path only."""
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, x1, x2, labels, temperature, gamma, mode, correct_grad, eps):
         _require_cuda(x1, x2, labels)
         if x1.shape != x2.shape or x1.dim() < 2:
@@ -357,15 +384,16 @@ class GraphRunner:
                                      bool(use_tc), n, d)
             return scalars, row_stats, dz
 
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                body()
-        torch.cuda.current_stream(device).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = body()
+        with torch.cuda.device(device):
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream(device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = body()
 
     def run(self, z1: Tensor, z2: Tensor, labels: Tensor):
         """-> static (scalars[4], row_stats[4, n_pad], dz[2n, d] for an upstream gradient of 1); overwritten by the
@@ -373,7 +401,8 @@ class GraphRunner:
         self.z1.copy_(z1)
         self.z2.copy_(z2)
         self.labels.copy_(labels)
-        self.graph.replay()
+        with torch.cuda.device(self.z1.device):
+            self.graph.replay()
         return self.out
 
 
@@ -412,6 +441,7 @@ def _odi(shape, dim: int):
 
 
 @torch.library.custom_op("spcl::l2norm_fwd", mutates_args=(), device_types="cuda")
+@on_device_of(0)
 def l2norm_fwd(x: Tensor, dim: int, eps: float) -> Tuple[Tensor, Tensor]:
     _require_cuda(x)
     if x.dtype not in _DTYPES:
@@ -434,6 +464,7 @@ def _(x, dim, eps):
 
 
 @torch.library.custom_op("spcl::l2norm_bwd", mutates_args=(), device_types="cuda")
+@on_device_of(1)
 def l2norm_bwd(gy: Tensor, y: Tensor, inv_norm: Tensor, dim: int) -> Tensor:
     _require_cuda(gy, y, inv_norm)
     gy = gy.contiguous().to(y.dtype)
@@ -475,6 +506,7 @@ class _DenseRows(torch.autograd.Function):
     """x [B, C, H, W] fp32 -> unit rows [B*P, C] (heads.py:109-115 + infonce.py:233-241 / comparable.py:398-404)."""
 
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, x, points, ph, pw, eps):
         _require_cuda(x, points)
         x = x.contiguous()
@@ -541,6 +573,7 @@ class _GroupSupCon(torch.autograd.Function):
     """fp32 label-form problems; inputs z1_0, z2_0, z1_1, z2_1, ...; outputs one scalars[4] per problem."""
 
     @staticmethod
+    @on_device_of(3)
     def forward(ctx, meta, labels, *views):
         K = len(meta)
         dev = views[0].device
@@ -646,20 +679,22 @@ class GroupGraphRunner:
             nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(self.probs), self.K, st)
             nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(self.probs), self.K, st)
 
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            for _ in range(2):
+        with torch.cuda.device(device):
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream(device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 body()
-        torch.cuda.current_stream(device).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            body()
 
     def run(self, flat_views, labels):
         torch._foreach_copy_(self.z_dst, list(flat_views))
         torch._foreach_copy_(self.lab_dst, [l for l in labels for _ in (0, 1)])
-        self.graph.replay()
+        with torch.cuda.device(self.ws.device):
+            self.graph.replay()
         return self.scalars, self.dz
 
 

@@ -393,7 +393,8 @@ def test_hostfeed_matches_direct_calls():
     for g, w in zip(got_g, want_g):
         # row sums and dZ are accumulated with atomics: same terms, different order; a last-bit change of a row
         # statistic can flip the bf16 rounding of a T element (2^-9 of that element)
-        assert (g - w).abs().max().item() <= 2e-4 * w.abs().max().item()
+        # (measured run to run: up to 3e-4 of max|g|; anything structural -- a stale slot, a wrong batch -- is O(1))
+        assert (g - w).abs().max().item() <= 1e-3 * w.abs().max().item()
     with pytest.raises(RuntimeError):
         for _ in range(3):
             feed.push(*pinned[0], lab_h)

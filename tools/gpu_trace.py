@@ -40,6 +40,7 @@ def dump(name, tr, ntiles=24, both=False):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    bwd_flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # debug switches for the backward pass only
     labels = torch.arange(n)
     g = torch.Generator().manual_seed(0)
     base = torch.randn(n, d, generator=g)
@@ -64,11 +65,14 @@ def main():
         ops.supcon_bwd(gone, zpack, labels_full, sig, None, row_stats, scalars, 0.07, 8.0, 0, True, n, d)
     torch.cuda.synchronize()
     tr.zero_()
+    h.spcl_debug_set_flags.argtypes = [ctypes.c_int]
+    h.spcl_debug_set_flags(bwd_flags)
     h.spcl_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
     ops.supcon_bwd(gone, zpack, labels_full, sig, None, row_stats, scalars, 0.07, 8.0, 0, True, n, d)
     torch.cuda.synchronize()
     h.spcl_debug_set_trace(None)
-    dump("bwd_kernel", tr)
+    h.spcl_debug_set_flags(0)
+    dump(f"bwd_kernel flags={bwd_flags}", tr, ntiles=40)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ using namespace spcl::ptx;
 constexpr int COUNT = 256;
 
 // variant: 0 SS N128 | 1 SS N256 | 2 TS N128 | 3 TS N256 | 4 SS N128, two D buffers alternating
-//          5 TS N128 with B read MN-major | 6 SS N64
+//          5 TS N128 with B read MN-major | 6 SS N64 | 7 SS N128 with B read MN-major
 __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, uns
   unsigned long long t0 = 0, t1 = 0;
   if (warp == 1) {
     const int n = (variant == 1 || variant == 3) ? 256 : (variant == 6 ? 64 : 128);
-    const uint32_t idesc = make_idesc_bf16(128, n, false, variant == 5);
+    const uint32_t idesc = make_idesc_bf16(128, n, false, variant == 5 || variant == 7);
     const uint32_t b_panel = (n == 256) ? 32768u : 16384u;
     __syncwarp();
     t0 = clock64();
@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, uns
           mma_ts(d, tmem + 256 + kk * 8, make_smem_desc_sw128(b_base + off_b, 16, 1024), idesc, i != 0);
         } else if (variant == 5) {
           mma_ts(d, tmem + 256 + kk * 8, make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024), idesc, i != 0);
+        } else if (variant == 7) {
+          mma_ss(d, make_smem_desc_sw128(a_base + off_a, 16, 1024), make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024),
+                 idesc, i != 0);
         } else {
           mma_ss(d, make_smem_desc_sw128(a_base + off_a, 16, 1024), make_smem_desc_sw128(b_base + off_b, 16, 1024),
                  idesc, i != 0);
@@ -84,10 +87,10 @@ int main() {
   const size_t smem = 32768 + 65536 + 1024;
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const char* names[] = {"SS M128 N128", "SS M128 N256", "TS M128 N128", "TS M128 N256", "SS N128 two D buffers",
-                         "TS N128, B MN-major", "SS M128 N64"};
+                         "TS N128, B MN-major", "SS M128 N64", "SS N128, B MN-major"};
   for (int noise : {0, 4000}) {
     for (int grid : {1, 148}) {
-      for (int v = 0; v < 7; ++v) {
+      for (int v = 0; v < 8; ++v) {
         bench<<<grid, 128, smem>>>(v, noise, d_out);
         bench<<<grid, 128, smem>>>(v, noise, d_out);
         cudaError_t e = cudaDeviceSynchronize();
