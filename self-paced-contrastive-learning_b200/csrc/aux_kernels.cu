@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 
 #include <climits>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -166,10 +167,189 @@ __global__ void __launch_bounds__(256) l2norm_strided_bwd(const T* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variants (the ones that run for the projector widths of the reference, d <= 512 rows /
+// d <= 256 NCHW): every element is read from HBM ONCE and written once.
+//
+// rows:    a warp takes R rows per iteration and issues all of their 16-byte loads before the first reduction
+//          (one row per warp per trip kept only ~0.5 KB in flight per warp: 3.3 TB/s at cfg4 sizes).
+// strided: a 256-thread CTA owns a tile of 16 * V consecutive `inner` positions of one image; thread (g, l) keeps
+//          channels g, g + 16, ... of its V positions in registers, the 16 channel groups meet through shared memory.
+//          (One thread per position walked all d channels serially: 32 CTAs for a [32, 128, 32, 32] tensor, 7 % of
+//          the copy bandwidth.)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V, int NV, int R>
+__global__ void __launch_bounds__(256) l2norm_rows_fwd_reg(const T* __restrict__ x, T* __restrict__ y,
+                                                           float* __restrict__ inv_norm, int64_t rows, int d,
+                                                           float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r0 = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * R; r0 < rows;
+       r0 += warps_total * R) {
+    Vec<T, V> v[R][NV];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * V;
+        if (r0 + i < rows && c < d) v[i][k] = *reinterpret_cast<const Vec<T, V>*>(x + (r0 + i) * d + c);
+        else
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[i][k].v[e] = from_f<T>(0.f);
+      }
+    float ss[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      ss[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < V; ++e) { const float f = to_f(v[i][k].v[e]); ss[i] = fmaf(f, f, ss[i]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < R; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (r0 + i >= rows) break;
+      const float inv = 1.f / fmaxf(sqrtf(ss[i]), eps);
+      if (lane == 0 && inv_norm != nullptr) inv_norm[r0 + i] = inv;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * V;
+        if (c < d) {
+          Vec<T, V> o;
+#pragma unroll
+          for (int e = 0; e < V; ++e) o.v[e] = from_f<T>(to_f(v[i][k].v[e]) * inv);
+          *reinterpret_cast<Vec<T, V>*>(y + (r0 + i) * d + c) = o;
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int V, int NV, int R>
+__global__ void __launch_bounds__(256) l2norm_rows_bwd_reg(const T* __restrict__ gy, const T* __restrict__ y,
+                                                           const float* __restrict__ inv_norm, T* __restrict__ gx,
+                                                           int64_t rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r0 = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * R; r0 < rows;
+       r0 += warps_total * R) {
+    Vec<T, V> a[R][NV], b[R][NV];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * V;
+        if (r0 + i < rows && c < d) {
+          a[i][k] = *reinterpret_cast<const Vec<T, V>*>(gy + (r0 + i) * d + c);
+          b[i][k] = *reinterpret_cast<const Vec<T, V>*>(y + (r0 + i) * d + c);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) { a[i][k].v[e] = from_f<T>(0.f); b[i][k].v[e] = from_f<T>(0.f); }
+        }
+      }
+    float dot[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      dot[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < V; ++e) dot[i] = fmaf(to_f(a[i][k].v[e]), to_f(b[i][k].v[e]), dot[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < R; ++i) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (r0 + i >= rows) break;
+      const float inv = inv_norm[r0 + i];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * V;
+        if (c < d) {
+          Vec<T, V> o;
+#pragma unroll
+          for (int e = 0; e < V; ++e) o.v[e] = from_f<T>(inv * (to_f(a[i][k].v[e]) - to_f(b[i][k].v[e]) * dot[i]));
+          *reinterpret_cast<Vec<T, V>*>(gx + (r0 + i) * d + c) = o;
+        }
+      }
+    }
+  }
+}
+
+constexpr int kStrG = 16, kStrL = 16;     // channel groups x lanes along `inner` of a strided tile (256 threads)
+
+// BWD = false: y = x * inv, inv_norm out.  BWD = true: gx = inv * (gy - y * sum_c(y gy)) with a = gy, b = y.
+template <typename T, int V, int KC, bool BWD>
+__global__ void __launch_bounds__(256) l2norm_strided_reg(const T* __restrict__ a_in, const T* __restrict__ b_in,
+                                                          T* __restrict__ out, float* __restrict__ inv_norm,
+                                                          int d, int64_t inner, int64_t tiles_per_image, float eps) {
+  __shared__ float part[kStrG][kStrL * V + 1];
+  const int g = threadIdx.x / kStrL, l = threadIdx.x % kStrL;
+  const int64_t o = blockIdx.x / tiles_per_image, t = blockIdx.x % tiles_per_image;
+  const int64_t p0 = t * (kStrL * V) + l * V;                 // first of this thread's V positions
+  const bool pos_ok = p0 < inner;                             // inner % V == 0: all V positions valid or none
+  const int64_t base = o * d * inner + p0;
+  Vec<T, V> a[KC], b[BWD ? KC : 1];
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kStrG * k;
+    if (pos_ok && c < d) {
+      a[k] = *reinterpret_cast<const Vec<T, V>*>(a_in + base + c * inner);
+      if (BWD) b[k] = *reinterpret_cast<const Vec<T, V>*>(b_in + base + c * inner);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float f = to_f(a[k].v[e]);
+        acc[e] = fmaf(f, BWD ? to_f(b[k].v[e]) : f, acc[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) part[g][l * V + e] = acc[e];
+  __syncthreads();
+  float tot[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    tot[e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < kStrG; ++q) tot[e] += part[q][l * V + e];
+  }
+  if (!pos_ok) return;
+  float inv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    if (BWD) {
+      inv[e] = inv_norm[o * inner + p0 + e];
+    } else {
+      inv[e] = 1.f / fmaxf(sqrtf(tot[e]), eps);
+      if (g == 0 && inv_norm != nullptr) inv_norm[o * inner + p0 + e] = inv[e];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kStrG * k;
+    if (c < d) {
+      Vec<T, V> w;
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        w.v[e] = BWD ? from_f<T>(inv[e] * (to_f(a[k].v[e]) - to_f(b[k].v[e]) * tot[e])) : from_f<T>(to_f(a[k].v[e]) * inv[e]);
+      *reinterpret_cast<Vec<T, V>*>(out + base + c * inner) = w;
+    }
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned grid_for(int64_t threads_needed) {
   int64_t blocks = ceil_div(threads_needed, 256);
-  const int64_t cap = 148LL * 16;     // 8 waves of 2 resident CTAs/SM is plenty for a streaming kernel
+  const int64_t cap = 148LL * 64;     // grid-stride loops: a few trips per warp at the largest sizes
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<unsigned>(blocks);
@@ -182,15 +362,33 @@ static int launch_fwd(const void* x, void* y, float* inv_norm, int64_t outer, in
   const T* xp = static_cast<const T*>(x);
   T* yp = static_cast<T*>(y);
   const bool al = aligned16(x) && aligned16(y);
+  static const bool legacy = getenv("SPCL_L2NORM_LEGACY") != nullptr;     // A/B switch: the pre-round-2 kernels
   if (inner == 1) {
     const unsigned grid = grid_for(outer * 32);
-    if (al && d % VMAX == 0) l2norm_rows_fwd<T, VMAX><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
-    else l2norm_rows_fwd<T, 1><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    const bool vec = al && d % VMAX == 0;
+    if (vec && !legacy && d <= 32 * VMAX) {
+      l2norm_rows_fwd_reg<T, VMAX, 1, 8><<<grid_for(ceil_div(outer, 8) * 32), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    } else if (vec && !legacy && d <= 64 * VMAX) {
+      l2norm_rows_fwd_reg<T, VMAX, 2, 4><<<grid_for(ceil_div(outer, 4) * 32), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    } else if (vec && !legacy && d <= 128 * VMAX) {
+      l2norm_rows_fwd_reg<T, VMAX, 4, 2><<<grid_for(ceil_div(outer, 2) * 32), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    } else if (vec) {
+      l2norm_rows_fwd<T, VMAX><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    } else {
+      l2norm_rows_fwd<T, 1><<<grid, 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, eps);
+    }
   } else {
-    if (al && inner % VMAX == 0)
+    const bool vec = al && inner % VMAX == 0;
+    const int64_t tiles = ceil_div(inner, static_cast<int64_t>(kStrL * VMAX));
+    if (vec && !legacy && d <= 8 * kStrG && outer * tiles <= INT_MAX) {
+      l2norm_strided_reg<T, VMAX, 8, false><<<static_cast<unsigned>(outer * tiles), 256, 0, s>>>(xp, nullptr, yp, inv_norm, (int)d, inner, tiles, eps);
+    } else if (vec && !legacy && d <= 16 * kStrG && outer * tiles <= INT_MAX) {
+      l2norm_strided_reg<T, VMAX, 16, false><<<static_cast<unsigned>(outer * tiles), 256, 0, s>>>(xp, nullptr, yp, inv_norm, (int)d, inner, tiles, eps);
+    } else if (vec) {
       l2norm_strided_fwd<T, VMAX><<<grid_for(outer * inner / VMAX), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, inner, eps);
-    else
+    } else {
       l2norm_strided_fwd<T, 1><<<grid_for(outer * inner), 256, 0, s>>>(xp, yp, inv_norm, outer, (int)d, inner, eps);
+    }
   }
   SPCL_LAUNCH_CHECK("spcl_l2norm_fwd");
   return SPCL_OK;
@@ -204,15 +402,31 @@ static int launch_bwd(const void* gy, const void* y, const float* inv_norm, void
   const T* yp = static_cast<const T*>(y);
   T* xp = static_cast<T*>(gx);
   const bool al = aligned16(gy) && aligned16(y) && aligned16(gx);
+  static const bool legacy = getenv("SPCL_L2NORM_LEGACY") != nullptr;     // A/B switch: the pre-round-2 kernels
   if (inner == 1) {
     const unsigned grid = grid_for(outer * 32);
-    if (al && d % VMAX == 0) l2norm_rows_bwd<T, VMAX><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
-    else l2norm_rows_bwd<T, 1><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    const bool vec = al && d % VMAX == 0;
+    if (vec && !legacy && d <= 32 * VMAX) {
+      l2norm_rows_bwd_reg<T, VMAX, 1, 4><<<grid_for(ceil_div(outer, 4) * 32), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    } else if (vec && !legacy && d <= 64 * VMAX) {
+      l2norm_rows_bwd_reg<T, VMAX, 2, 2><<<grid_for(ceil_div(outer, 2) * 32), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    } else if (vec && !legacy && d <= 128 * VMAX) {
+      l2norm_rows_bwd_reg<T, VMAX, 4, 1><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    } else if (vec) {
+      l2norm_rows_bwd<T, VMAX><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    } else {
+      l2norm_rows_bwd<T, 1><<<grid, 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d);
+    }
   } else {
-    if (al && inner % VMAX == 0)
+    const bool vec = al && inner % VMAX == 0;
+    const int64_t tiles = ceil_div(inner, static_cast<int64_t>(kStrL * VMAX));
+    if (vec && !legacy && d <= 8 * kStrG && outer * tiles <= INT_MAX) {
+      l2norm_strided_reg<T, VMAX, 8, true><<<static_cast<unsigned>(outer * tiles), 256, 0, s>>>(gp, yp, xp, const_cast<float*>(inv_norm), (int)d, inner, tiles, 0.f);
+    } else if (vec) {
       l2norm_strided_bwd<T, VMAX><<<grid_for(outer * inner / VMAX), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d, inner);
-    else
+    } else {
       l2norm_strided_bwd<T, 1><<<grid_for(outer * inner), 256, 0, s>>>(gp, yp, inv_norm, xp, outer, (int)d, inner);
+    }
   }
   SPCL_LAUNCH_CHECK("spcl_l2norm_bwd");
   return SPCL_OK;

@@ -1,0 +1,117 @@
+"""HBM roofline of the memory-bound kernels next to the fused loss, device-timed:
+
+    python tools/gpu_aux_bench.py > gpurun_out/aux_bench.json
+
+  l2norm rows / NCHW fwd + bwd (``spcl_l2norm_fwd/bwd``, projectors/nn.py:35-36)
+  prepare (``spcl_supcon_prepare_bf16``: cat + bf16 pack + labels + signatures)
+  prepare_raw / raw_bwd (``spcl_supcon_prepare_raw_bf16`` / ``spcl_supcon_raw_bwd``: fused projector tail, f1)
+
+Shapes: the cfg3 operands ([32, 128, 32, 32] NCHW = [32768, 128] rows, 16.8 MB: smaller than the 126 MB L2, so each run
+follows a 256 MB L2 flush and is launch-latency dominated: 16.8 MB move in 2.6 us at the measured copy bandwidth,
+next to ~2-3 us of launch) and the cfg4-sized operands ([262144, 128] = 134 MB per tensor, > L2: streamed, no flush).
+Algorithmic bytes = every input read once + every output written once.  ``frac`` is against MEASURED_PEAKS.json hbm_gbs.
+"""
+import ctypes
+import json
+import pathlib
+import sys
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import spcl_b200                                            # noqa: E402
+from spcl_b200 import _native as nat                        # noqa: E402
+from spcl_b200 import ops                                   # noqa: E402
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6534.8
+
+
+def timed(fn, reps=20, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def _case(name, shape, nbytes, fn, flush):
+    ms = timed(fn, flush=flush)
+    return dict(kernel=name, shape=list(shape), bytes=nbytes, us=ms * 1e3, gbs=nbytes / ms / 1e6,
+                frac=nbytes / ms / 1e6 / PEAK, l2="256 MB flush" if flush is not None else "operands > L2, streamed")
+
+
+def measure(big: bool = True):
+    dev = "cuda"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    shapes = [("cfg3", (32768, 128), (32, 128, 32, 32))]
+    if big:
+        shapes.append(("cfg4", (262144, 128), (256, 128, 32, 32)))
+    for tag, rows_shape, nchw_shape in shapes:
+        fl = flush if tag == "cfg3" else None
+        N, d = rows_shape
+        # ---- l2norm, rows layout [N, d] ----
+        x = torch.randn(N, d, device=dev)
+        ycopy = torch.empty_like(x)
+        # context: what a plain device copy of the same size reaches when timed the same way (the roofline denominator
+        # was measured on a 4 GB copy; at 17 - 134 MB per tensor ramp-up and launch are a visible share)
+        out.append(_case(f"torch_copy_same_size[{tag}]", rows_shape, 8 * N * d, lambda: ycopy.copy_(x), fl))
+        out.append(_case(f"torch_F_normalize[{tag}]", rows_shape, 8 * N * d, lambda: torch.nn.functional.normalize(x, dim=1), fl))
+        y, inv = ops.l2norm_fwd(x, 1, 1e-12)
+        gy = torch.randn_like(x)
+        out.append(_case(f"l2norm_rows_fwd[{tag}]", rows_shape, 8 * N * d + 4 * N, lambda: ops.l2norm_fwd(x, 1, 1e-12), fl))
+        out.append(_case(f"l2norm_rows_bwd[{tag}]", rows_shape, 12 * N * d + 4 * N, lambda: ops.l2norm_bwd(gy, y, inv, 1), fl))
+        # ---- l2norm, NCHW (DenseProjectionHead, heads.py:113-114) ----
+        xs = torch.randn(*nchw_shape, device=dev)
+        ys, invs = ops.l2norm_fwd(xs, 1, 1e-12)
+        gys = torch.randn_like(xs)
+        nel = xs.numel()
+        out.append(_case(f"l2norm_strided_fwd[{tag}]", nchw_shape, 8 * nel + 4 * nel // nchw_shape[1],
+                         lambda: ops.l2norm_fwd(xs, 1, 1e-12), fl))
+        out.append(_case(f"l2norm_strided_bwd[{tag}]", nchw_shape, 12 * nel + 4 * nel // nchw_shape[1],
+                         lambda: ops.l2norm_bwd(gys, ys, invs, 1), fl))
+        # ---- prepare: two fp32 views -> packed bf16 + labels + signatures ----
+        n = N // 2
+        z1, z2 = y[:n].contiguous(), y[n:].contiguous()
+        labels = torch.arange(n, dtype=torch.int32, device=dev)
+        zpack = torch.empty(N, d, dtype=torch.bfloat16, device=dev)
+        labels_full = torch.empty(N, dtype=torch.int32, device=dev)
+        sig = torch.empty(N // 128, 4, dtype=torch.int32, device=dev)
+        partials = torch.empty(4, dtype=torch.float32, device=dev)
+        st = ops._stream(z1)
+        P = ops._ptr
+        out.append(_case(f"prepare_kernel[{tag}]", rows_shape, 4 * N * d + 2 * N * d + 8 * N,
+                         lambda: nat.call("spcl_supcon_prepare_bf16", P(z1), P(z2), n, d, d, d, P(labels), P(zpack), N, d,
+                                          P(labels_full), P(sig), P(partials), st), fl))
+        # ---- fused projector tail (f1): raw NCHW projector outputs -> packed bf16 rows; and its backward ----
+        B, C, H, W = nchw_shape
+        x1 = torch.randn(B // 2, C, H, W, device=dev)
+        x2 = torch.randn(B // 2, C, H, W, device=dev)
+        inv_norm = torch.empty(N, dtype=torch.float32, device=dev)
+        out.append(_case(f"prepare_raw_kernel[{tag}]", nchw_shape, 4 * N * d + 2 * N * d + 12 * N,
+                         lambda: nat.call("spcl_supcon_prepare_raw_bf16", P(x1), P(x2), B // 2, C, H * W, ctypes.c_float(1e-12),
+                                          P(labels), P(zpack), N, d, P(inv_norm), P(labels_full), P(sig), P(partials), st), fl))
+        dz = torch.randn(N, d, device=dev)
+        gx1, gx2 = torch.empty_like(x1), torch.empty_like(x2)
+        out.append(_case(f"raw_bwd_kernel[{tag}]", nchw_shape, 4 * N * d * 3 + 4 * N,
+                         lambda: nat.call("spcl_supcon_raw_bwd", P(dz), d, P(x1), P(x2), P(inv_norm), P(gx1), P(gx2),
+                                          B // 2, C, H * W, st), fl))
+        del x, y, gy, xs, ys, gys, zpack, x1, x2, dz, gx1, gx2
+        torch.cuda.empty_cache()
+    # launch floor: an empty-ish launch timed the same way, to read the cfg3 numbers against
+    t = torch.empty(1, device=dev)
+    floor = timed(lambda: t.zero_(), flush=flush)
+    return dict(peak_gbs=PEAK, launch_floor_us=floor * 1e3, cases=out)
+
+
+if __name__ == "__main__":
+    print(json.dumps(measure()))
