@@ -174,6 +174,21 @@ int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_pad, int32_t
                          const float* grad_out, int64_t row_begin, int64_t row_end, float inv_tau, float gamma,
                          int mode, float* dz, int64_t lddz, void* zt, spcl_stream_t stream);
 
+/* ---- soft positive weights: SupConLoss3 / SupConLoss4 (contrastyou/losses/contrast_loss.py:130-270) and
+ * SupConLoss2's "in" mode (:33-100), fp32 operands --------------------------------------------------------------
+ * A pair (i, j), j != i, carries the weight pw[i % pwn][j % pwn] (pwn = N/2: SupConLoss3's pos_weight.repeat(2, 2),
+ * :152; pwn = N: SupConLoss4's assembled matrix, :214-227) and enters the denominator iff enable == NULL or
+ * enable[i][j] != 0 (uint8 [N][N], SupConLoss4's enable_mask, :246).  in_mode 0: l_i = sum_j w_ij (S_ij - logD_i) / W_i
+ * (:173-176); in_mode 1: l_i = log(sum_j w_ij E_ij / rowsum_i) / W_i (:168-171); loss = -(1/N) sum_i l_i through
+ * spcl_supcon_finalize (partials zeroed by the caller).  No gradient flows to pw. */
+int spcl_supcon_fwd_w_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const float* pw, int64_t pwn,
+                          const uint8_t* enable, int in_mode, float inv_tau, float* row_stats, int64_t stats_stride,
+                          float* partials, spcl_stream_t stream);
+int spcl_supcon_bwd_w_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const float* pw, int64_t pwn,
+                          const uint8_t* enable, int in_mode, float inv_tau, const float* row_stats,
+                          int64_t stats_stride, const float* scalars, const float* grad_out, float* dz, int64_t lddz,
+                          spcl_stream_t stream);
+
 /* ---- fp32 SIMT path: same contract with fp32 operands, exact-parity mode ----------------------
  * z: float [n_total][ldz].  Exactly one of labels / tri may be non-NULL (tri needs n_half = N/2). */
 int spcl_supcon_fwd_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,

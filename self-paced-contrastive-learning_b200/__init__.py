@@ -9,10 +9,11 @@ from ._native import LIB_PATH, SpclError, build
 from . import dense, hooks
 from .dense import DenseProjectionTail, point_coordinates, region_extractor
 from .hostfeed import HostFeed
-from .losses import SelfPacedSupConLoss, SupConLoss1, grouped_forward, is_normalized, supcon_loss
+from .losses import (SelfPacedSupConLoss, SupConLoss1, SupConLoss2, SupConLoss3, SupConLoss4, grouped_forward,
+                     is_normalized, supcon_loss)
 from .projectors import Normalize, normalize
 from .schedule import PScheduler
 
-__all__ = ["SelfPacedSupConLoss", "SupConLoss1", "supcon_loss", "grouped_forward", "is_normalized", "Normalize", "normalize",
+__all__ = ["SelfPacedSupConLoss", "SupConLoss1", "SupConLoss2", "SupConLoss3", "SupConLoss4", "supcon_loss", "grouped_forward", "is_normalized", "Normalize", "normalize",
            "PScheduler", "HostFeed", "DenseProjectionTail", "point_coordinates", "region_extractor", "dense", "hooks", "build", "LIB_PATH", "SpclError"]
 __version__ = "0.1.0"

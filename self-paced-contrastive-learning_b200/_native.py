@@ -50,6 +50,9 @@ SIGNATURES = {
                                   _ptr, _ptr],
     "spcl_supcon_bwd_f32_split": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _f32, _f32,
                                   _c.c_int, _ptr, _i64, _ptr],
+    "spcl_supcon_fwd_w_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _ptr, _c.c_int, _f32, _ptr, _i64, _ptr, _ptr],
+    "spcl_supcon_bwd_w_f32": [_ptr, _i64, _i32, _i64, _ptr, _i64, _ptr, _c.c_int, _f32, _ptr, _i64, _ptr, _ptr, _ptr,
+                              _i64, _ptr],
     "spcl_supcon_finalize": [_ptr, _i64, _c.c_int, _ptr, _ptr],
     "spcl_supcon_group_fwd_f32": [_ptr, _c.c_int, _ptr],
     "spcl_supcon_group_bwd_f32": [_ptr, _c.c_int, _ptr],

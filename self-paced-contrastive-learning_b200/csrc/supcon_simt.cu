@@ -335,6 +335,175 @@ __global__ void __launch_bounds__(NT) bwd_kernel(Args p, const float* __restrict
 }
 
 // =================================================================================================
+// Soft positive weights: SupConLoss3 / SupConLoss4 (contrastyou/losses/contrast_loss.py:130-270) and SupConLoss2's
+// "in" mode (:33-100).  A pair (i, j), j != i, carries a real weight w_ij = pw[i % pwn][j % pwn] instead of a 0/1
+// positive flag, and enters the denominator iff enable == NULL or enable[i][j] != 0 (SupConLoss4's enable_mask).
+//   out mode:  l_i = sum_j w_ij (S_ij - logD_i) / W_i                 (:173-176, :255-258)
+//   in mode :  l_i = log(sum_j w_ij E_ij / rowsum_i) / W_i            (:168-171, :250-253),   W_i = sum_j w_ij
+//   loss = -(1/N) sum_i l_i.   Row-grid kernels like fwd_kernel / bwd_kernel above (these losses run at the
+//   reference's batch sizes; the weight matrix is N x N by nature).
+// row_stats planes: 0 logD_i | 1 1/W_i | 2 v_i = in ? 1/(W_i q_i) : 0 | 3 u_i = out ? 1/rowsum_i : 1/(W_i rowsum_i)
+//   T_ij = en_ij E u_i + en_ji E u_j - (out ? w_ij/W_i + w_ji/W_j : E (w_ij v_i + w_ji v_j))
+// =================================================================================================
+struct WArgs {
+  const float* pw;
+  int64_t pwn;
+  const uint8_t* en;
+  int in_mode;
+};
+
+__device__ __forceinline__ float w_of(const WArgs& w, int64_t gi, int64_t gj) {
+  return w.pw[(gi % w.pwn) * w.pwn + (gj % w.pwn)];
+}
+__device__ __forceinline__ bool en_of(const WArgs& w, int64_t N, int64_t gi, int64_t gj) {
+  return w.en == nullptr || w.en[gi * N + gj] != 0;
+}
+
+__global__ void __launch_bounds__(NT) fwdw_kernel(Args p, WArgs w, float* __restrict__ row_stats, int64_t sld,
+                                                  float* __restrict__ partials) {
+  __shared__ Smem sm;
+  __shared__ float red[2][BM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+  int64_t gi[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) gi[a] = i0 + ty * 4 + a;
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][4];
+  for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
+    tile_dot(p, sm, i0, j0, acc);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t gj = j0 + tx + 16 * b;
+      if (gj >= p.N) continue;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (gi[a] == gj || gi[a] >= p.N) continue;
+        const float s = acc[a][b] * p.inv_tau;
+        const float e = expf(s - shift);
+        const float wij = w_of(w, gi[a], gj);
+        if (en_of(w, p.N, gi[a], gj)) rowsum[a] += e;
+        wsum[a] += wij;
+        sx[a] = fmaf(wij, w.in_mode ? e : s, sx[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    rowsum[a] = row_sum16(rowsum[a]);
+    wsum[a] = row_sum16(wsum[a]);
+    sx[a] = row_sum16(sx[a]);
+  }
+  if (tx == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = ty * 4 + a;
+      float l = 0.f, ws = 0.f;
+      if (gi[a] < p.row_end) {
+        const float logD = shift + logf(rowsum[a]);
+        const float invw = 1.f / wsum[a];            // W_i == 0 -> inf -> NaN loss, like the reference's 0/0
+        l = w.in_mode ? logf(sx[a] / rowsum[a]) * invw : (sx[a] - wsum[a] * logD) * invw;
+        ws = wsum[a];
+        row_stats[gi[a]] = logD;
+        row_stats[sld + gi[a]] = invw;
+        row_stats[2 * sld + gi[a]] = w.in_mode ? invw / sx[a] : 0.f;
+        row_stats[3 * sld + gi[a]] = w.in_mode ? invw / rowsum[a] : 1.f / rowsum[a];
+      }
+      red[0][r] = l;
+      red[1][r] = ws;
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, lane = tid & 31;
+    float v = red[which][lane] + red[which][lane + 32];
+    v = warp_sum(v);
+    if (lane == 0) {
+      atomicAdd(&partials[which], v);
+      if (which == 1) atomicAdd(&partials[2], v);      // ratio = 1: there is no self-paced weighting here
+    }
+  }
+}
+
+template <int DV>
+__global__ void __launch_bounds__(NT) bwdw_kernel(Args p, WArgs w, const float* __restrict__ row_stats, int64_t sld,
+                                                  const float* __restrict__ scalars,
+                                                  const float* __restrict__ grad_out, float* __restrict__ dz,
+                                                  int64_t lddz) {
+  __shared__ Smem sm;
+  __shared__ float ts[BM][BN + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = p.row_begin + static_cast<int64_t>(blockIdx.x) * BM;
+  const float shift = p.inv_tau;
+  int64_t gi[4];
+  float3 si[4];                                          // 1/W, v, u
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    gi[a] = i0 + ty * 4 + a;
+    si[a] = gi[a] < p.N ? make_float3(row_stats[sld + gi[a]], row_stats[2 * sld + gi[a]], row_stats[3 * sld + gi[a]])
+                        : make_float3(0.f, 0.f, 0.f);
+  }
+  float dzacc[4][DV];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < DV; ++c) dzacc[a][c] = 0.f;
+  float acc[4][4];
+  for (int64_t j0 = 0; j0 < p.N; j0 += BN) {
+    tile_dot(p, sm, i0, j0, acc);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int cj = tx + 16 * b;
+      const int64_t gj = j0 + cj;
+      const bool col_ok = gj < p.N;
+      const float3 sj = col_ok ? make_float3(row_stats[sld + gj], row_stats[2 * sld + gj], row_stats[3 * sld + gj])
+                               : make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float t = 0.f;
+        if (col_ok && gi[a] < p.N && gi[a] != gj) {
+          const float e = expf(acc[a][b] * p.inv_tau - shift);
+          const float wij = w_of(w, gi[a], gj), wji = w_of(w, gj, gi[a]);
+          if (en_of(w, p.N, gi[a], gj)) t = fmaf(e, si[a].z, t);
+          if (en_of(w, p.N, gj, gi[a])) t = fmaf(e, sj.z, t);
+          if (w.in_mode) t -= e * fmaf(wij, si[a].y, wji * sj.y);
+          else t -= fmaf(wij, si[a].x, wji * sj.x);
+        }
+        ts[ty * 4 + a][cj] = t;
+      }
+    }
+    __syncthreads();
+    const int jmax = static_cast<int>(min(static_cast<int64_t>(BN), p.N - j0));
+    for (int jj = 0; jj < jmax; ++jj) {
+      const float* zrow = p.z + (j0 + jj) * p.ldz;
+      float t[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) t[a] = ts[ty * 4 + a][jj];
+#pragma unroll
+      for (int c = 0; c < DV; ++c) {
+        const int col = tx + 16 * c;
+        const float zv = col < p.d ? zrow[col] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dzacc[a][c] = fmaf(t[a], zv, dzacc[a][c]);
+      }
+    }
+    __syncthreads();
+  }
+  const float coef = grad_out[0] * scalars[3] * p.inv_tau;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (gi[a] >= p.row_end) continue;
+    float* out = dz + (gi[a] - p.row_begin) * lddz;
+#pragma unroll
+    for (int c = 0; c < DV; ++c) {
+      const int col = tx + 16 * c;
+      if (col < p.d) out[col] = dzacc[a][c] * coef;
+    }
+  }
+}
+
+// =================================================================================================
 // Split kernels for the label form (modes NONE / HARD / SOFT): the (row block, column range) grid instead of one
 // CTA per 64 rows.  The reference's own batch sizes (N = 60 .. 512) give the row-only grid 1 .. 8
 // CTAs on 148 SMs, each walking every column twice: 500 us per N = 512 problem, all latency.  Here a CTA owns one
@@ -704,6 +873,50 @@ extern "C" int spcl_supcon_bwd_f32(const float* z, int64_t n_total, int32_t d, i
   else if (d <= 128) simt::bwd_kernel<8><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
   else simt::bwd_kernel<16><<<grid, simt::NT, 0, s>>>(a, row_stats, stats_stride, scalars, grad_out, dz, lddz);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_f32");
+  return SPCL_OK;
+}
+
+// ---- soft positive weights (SupConLoss3 / SupConLoss4 / SupConLoss2 in-mode) --------------------------------------
+static int check_w(const float* z, int64_t n_total, int32_t d, int64_t ldz, const float* pw, int64_t pwn, float inv_tau,
+                   int in_mode) {
+  if (z == nullptr || pw == nullptr || n_total <= 0 || d <= 0 || ldz < d) return SPCL_ERR_INVALID_ARG;
+  if (d > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
+  if (pwn <= 0 || n_total % pwn != 0) return SPCL_ERR_INVALID_ARG;
+  if (!(inv_tau > 0.f) || (in_mode != 0 && in_mode != 1)) return SPCL_ERR_INVALID_ARG;
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_fwd_w_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const float* pw,
+                                     int64_t pwn, const uint8_t* enable, int in_mode, float inv_tau,
+                                     float* row_stats, int64_t stats_stride, float* partials, spcl_stream_t stream) {
+  int rc = check_w(z, n_total, d, ldz, pw, pwn, inv_tau, in_mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || partials == nullptr || stats_stride < n_total) return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, nullptr, nullptr, 0, 0, n_total, inv_tau, 1.f, 1.f, SPCL_MODE_NONE};
+  simt::WArgs w{pw, pwn, enable, in_mode};
+  const unsigned grid = static_cast<unsigned>(ceil_div(n_total, simt::BM));
+  simt::fwdw_kernel<<<grid, simt::NT, 0, static_cast<cudaStream_t>(stream)>>>(a, w, row_stats, stats_stride, partials);
+  SPCL_LAUNCH_CHECK("spcl_supcon_fwd_w_f32");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_supcon_bwd_w_f32(const float* z, int64_t n_total, int32_t d, int64_t ldz, const float* pw,
+                                     int64_t pwn, const uint8_t* enable, int in_mode, float inv_tau,
+                                     const float* row_stats, int64_t stats_stride, const float* scalars,
+                                     const float* grad_out, float* dz, int64_t lddz, spcl_stream_t stream) {
+  int rc = check_w(z, n_total, d, ldz, pw, pwn, inv_tau, in_mode);
+  if (rc != SPCL_OK) return rc;
+  if (row_stats == nullptr || scalars == nullptr || grad_out == nullptr || dz == nullptr || lddz < d ||
+      stats_stride < n_total)
+    return SPCL_ERR_INVALID_ARG;
+  simt::Args a{z, n_total, d, ldz, nullptr, nullptr, 0, 0, n_total, inv_tau, 1.f, 1.f, SPCL_MODE_NONE};
+  simt::WArgs w{pw, pwn, enable, in_mode};
+  const unsigned grid = static_cast<unsigned>(ceil_div(n_total, simt::BM));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d <= 64) simt::bwdw_kernel<4><<<grid, simt::NT, 0, s>>>(a, w, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else if (d <= 128) simt::bwdw_kernel<8><<<grid, simt::NT, 0, s>>>(a, w, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  else simt::bwdw_kernel<16><<<grid, simt::NT, 0, s>>>(a, w, row_stats, stats_stride, scalars, grad_out, dz, lddz);
+  SPCL_LAUNCH_CHECK("spcl_supcon_bwd_w_f32");
   return SPCL_OK;
 }
 

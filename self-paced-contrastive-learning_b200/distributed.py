@@ -4,12 +4,13 @@ The reference is single-process; this is additive.  Every rank holds the two vie
 samples (``z1``, ``z2``: ``[n_loc, d]``) and owns the anchor rows of those samples against ALL
 columns:
 
-  forward : pack local operands -> all-gather Z (bf16) and the labels -> pass A (row sums of exp(S), positive
-            counts): the tile triangle on / right of the diagonal is cut into `world` equal shares, every
-            rank runs one share (S is symmetric: a tile yields its row AND column sums) and the sums are
-            all-reduced (16 B per anchor) -> self-paced pass + row statistics on the owned rows ->
-            all-reduce of the three partial sums -> loss / ratio / scale on every rank;
-            all-gather of the per-row statistics for the backward.
+  forward : pack local operands -> all-gather Z (bf16) and the labels (one coalesced launch) -> pass A (row sums
+            of exp(S), positive counts): the tile triangle on / right of the diagonal is cut into `world` equal
+            shares, every rank runs one share (S is symmetric: a tile yields its row AND column sums) and the
+            sums are all-reduced (16 B per anchor) -> self-paced pass + row statistics on the owned rows ->
+            ONE all-gather of the per-row statistics for the backward with the rank's three partial sums
+            appended; the partial sums are added locally -> loss / ratio / scale on every rank.
+            Three collective launches per forward (round 1: five), none in the backward.
   backward: fused backward on the owned rows.  T = dS + dS^T is formed per tile from both blocks'
             statistics, so each rank ends with exactly the gradient rows of its own embeddings:
             no reduce-scatter of gradients is needed.
@@ -114,6 +115,28 @@ def _gather_rows(local: Tensor, world: int, group) -> Tensor:
     return out
 
 
+_COALESCE_OK = {}
+
+
+def _gather_pair(a: Tensor, b: Tensor, world: int, group):
+    """All-gather of two tensors (the operands and their labels) as ONE collective launch where the backend can
+    coalesce (NCCL group call); two plain all-gathers otherwise (gloo in the CPU tests)."""
+    outs = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in (a, b)]
+    key = dist.get_backend(group)
+    if _COALESCE_OK.get(key, key == "nccl"):
+        try:
+            with dist._coalescing_manager(group=group, device=a.device, async_ops=False):
+                dist.all_gather_into_tensor(outs[0], a.contiguous(), group=group)
+                dist.all_gather_into_tensor(outs[1], b.contiguous(), group=group)
+            _COALESCE_OK[key] = True
+            return outs
+        except Exception:                                    # noqa: BLE001  (API absent / unsupported backend)
+            _COALESCE_OK[key] = False
+    dist.all_gather_into_tensor(outs[0], a.contiguous(), group=group)
+    dist.all_gather_into_tensor(outs[1], b.contiguous(), group=group)
+    return outs
+
+
 class _ShardedSupCon(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z1, z2, labels, temperature, gamma, mode, correct_grad, group, backend):
@@ -123,13 +146,21 @@ class _ShardedSupCon(torch.autograd.Function):
         backend.check(plan, d)
         inv_tau = 1.0 / float(temperature)
         z_loc = backend.pack(z1.contiguous(), z2.contiguous())
-        z_all = _gather_rows(z_loc, world, group)                       # N * d_pad * 2 B over NVLink
-        labels_all = _gather_rows(torch.cat([labels, labels]), world, group)
+        # collective 1: operands (N * d_pad * 2 B over NVLink) and labels, one launch
+        z_all, labels_all = _gather_pair(z_loc, torch.cat([labels, labels]), world, group)
+        # (collective 2 is inside forward_rows: the all-reduce of the pass-A row sums)
         stats_loc, partials, sig = backend.forward_rows(z_all, labels_all, plan, inv_tau, float(gamma), int(mode), group)
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)    # 3 floats
+        # collective 3: every rank's [4, rows_loc] statistics planes AND its three partial sums travel in one
+        # all-gather (16 B per anchor + 16 B per rank); the partial sums are then added locally, in rank order, so
+        # every rank finalises the same loss / ratio / scale bit for bit -- no separate all-reduce of 3 floats
+        rows = plan.rows_loc
+        tail = torch.zeros(4 * rows + 4, dtype=stats_loc.dtype, device=stats_loc.device)
+        tail[:4 * rows] = stats_loc.reshape(-1)
+        tail[4 * rows:4 * rows + 3] = partials.to(stats_loc.dtype)
+        gathered = _gather_rows(tail[None], world, group)               # [world, 4 * rows + 4]
+        partials = gathered[:, 4 * rows:4 * rows + 3].sum(0).to(partials.dtype)
         scalars = backend.finalize(partials, plan.N, bool(correct_grad))
-        # 16 B per anchor; ranks contribute [4, rows_loc] plane slices -> [4, N] planes
-        stats_all = _gather_rows(stats_loc, world, group).view(world, 4, -1).permute(1, 0, 2).reshape(4, -1).contiguous()
+        stats_all = gathered[:, :4 * rows].reshape(world, 4, rows).permute(1, 0, 2).reshape(4, -1).contiguous()
         ctx.save_for_backward(z_all, labels_all, sig, stats_all, scalars)
         ctx.meta = (plan, inv_tau, float(gamma), int(mode), d, backend)
         ctx.mark_non_differentiable(scalars)

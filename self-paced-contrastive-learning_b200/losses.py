@@ -35,7 +35,8 @@ from torch import Tensor, nn
 from . import _native as nat
 from . import ops
 
-__all__ = ["SupConLoss1", "SelfPacedSupConLoss", "supcon_loss", "is_normalized", "grouped_forward"]
+__all__ = ["SupConLoss1", "SelfPacedSupConLoss", "SupConLoss2", "SupConLoss3", "SupConLoss4", "supcon_loss",
+           "is_normalized", "grouped_forward"]
 
 _AUTO_TC_MIN_N = 1024
 _DIAG_MAX_N = 16384
@@ -334,6 +335,108 @@ class SelfPacedSupConLoss(_FusedSupConBase):
         return self._ratio_cache
 
     sp_mask = property(lambda self: self._diag_get("sp_mask"))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# soft positive weights: the older loss generation, contrastyou/losses/contrast_loss.py
+# ----------------------------------------------------------------------------------------------------------------
+class _WeightedBase(nn.Module):
+    """Shared surface of ``SupConLoss2/3/4`` (contrast_loss.py:33-270): ``__init__(temperature=0.07, out_mode=True)``,
+    ``RuntimeError`` on a NaN loss (:98-99), ``sim_exp`` / ``sim_logits`` / ``pos_weight`` kept lazily for the
+    ``register_writer`` figures.  The arithmetic runs in ``spcl_supcon_fwd_w_f32`` / ``_bwd_w_f32`` (fp32 kernels:
+    these losses carry an N x N weight matrix by nature and run at the reference's batch sizes)."""
+
+    def __init__(self, temperature=0.07, out_mode=True, **kwargs):
+        super().__init__()
+        self._t = temperature
+        self._out_mode = out_mode
+        self._check_nan = bool(kwargs.pop("check_nan", True))
+        self._validate = bool(kwargs.pop("validate", True))
+        self._last = None
+
+    def _run(self, proj_feat1, proj_feat2, pw, enable):
+        if self._validate:
+            assert is_normalized(proj_feat1) and is_normalized(proj_feat2), "features need to be normalized first"
+        assert proj_feat1.shape == proj_feat2.shape, (proj_feat1.shape, proj_feat2.shape)
+        if not (proj_feat1.is_cuda and proj_feat2.is_cuda):
+            raise RuntimeError("spcl_b200 runs on CUDA tensors only: there is no CPU path")
+        loss = ops.supcon_weighted(proj_feat1, proj_feat2, pw, enable, self._t, not self._out_mode)
+        self._last = (proj_feat1.detach(), proj_feat2.detach())
+        if self._check_nan and torch.isnan(loss):
+            raise RuntimeError(loss)
+        return loss
+
+    def _logits(self):
+        if self._last is None:
+            raise AttributeError("only available after a forward call")
+        z = torch.cat(self._last).float()
+        logits = (z @ z.t()) / self._t
+        return logits - logits.max()
+
+    sim_logits = property(lambda self: self._logits())
+    sim_exp = property(lambda self: torch.exp(self._logits()))
+
+
+class SupConLoss2(_WeightedBase):
+    """contrast_loss.py:33-100: label / tri-state ``mask`` form with the "in" (``out_mode=False``, :90-92) or "out"
+    (:94-97) placement of the logarithm."""
+
+    def forward(self, proj_feat1, proj_feat2, target=None, mask: Tensor = None):
+        if (target is not None) and (mask is not None):
+            raise RuntimeError("`target` and `mask` should not be provided in the same time")      # :52-53
+        n, dev = proj_feat1.shape[0], proj_feat2.device
+        if mask is not None:
+            assert mask.shape == torch.Size([n, n])
+            m = mask.to(dev)
+            pos, neg = (m == 1), (m == 0)
+        elif target is not None:
+            codes = ops.label_codes(target, n, dev)
+            pos = codes[:, None] == codes[None, :]
+            neg = ~pos
+        else:
+            pos = torch.eye(n, dtype=torch.bool, device=dev)
+            neg = ~pos
+        self.pos_mask, self.neg_mask = pos.repeat(2, 2), neg.repeat(2, 2)
+        enable = (pos | neg).repeat(2, 2).to(torch.uint8)             # pairs of the denominator: pos + negs (:85-92)
+        return self._run(proj_feat1, proj_feat2, pos.float(), enable)
+
+
+class SupConLoss3(_WeightedBase):
+    """contrast_loss.py:130-182 ("soften supervised contrastive loss"): ``pos_weight`` [n, n], tiled 2 x 2 (:152)."""
+
+    def forward(self, proj_feat1, proj_feat2, pos_weight: Tensor = None, **kwargs):
+        assert pos_weight is not None
+        n = len(proj_feat1)
+        assert pos_weight.shape == torch.Size([n, n])
+        pw = pos_weight.detach().to(proj_feat2.device, torch.float32)
+        self.pos_weight = pw.repeat(2, 2)
+        return self._run(proj_feat1, proj_feat2, pw, None)
+
+
+class SupConLoss4(_WeightedBase):
+    """contrast_loss.py:206-262: separate weight blocks within view 1, within view 2 and across the views; pairs of a
+    block that was not given are left out of the denominator (``enable_mask``, :246).  The reference fills the
+    view-1 block only when ``one2two_weight`` is given (:217-219); that is kept."""
+
+    def forward(self, *, proj_feat1, proj_feat2, one2one_weight: Tensor = None, two2two_weight: Tensor,  # noqa
+                one2two_weight=None, **kwargs):  # noqa
+        assert one2one_weight is not None or one2two_weight is not None or two2two_weight is not None
+        n, dev = len(proj_feat1), proj_feat2.device
+        pw = torch.zeros(2 * n, 2 * n, device=dev, dtype=torch.float32)
+        en = torch.zeros(2 * n, 2 * n, device=dev, dtype=torch.uint8)
+        if one2two_weight is not None:                              # (sic) :217
+            pw[:n, :n] = one2one_weight
+            en[:n, :n] = 1
+        if two2two_weight is not None:
+            pw[n:, n:] = two2two_weight
+            en[n:, n:] = 1
+        if one2two_weight is not None:
+            pw[:n, n:] = one2two_weight
+            pw[n:, :n] = one2two_weight
+            en[:n, n:] = 1
+            en[n:, :n] = 1
+        self.pos_weight, self.enable_mask = pw, en.float()
+        return self._run(proj_feat1, proj_feat2, pw, en)
 
 
 _GROUP_GRAPHS: dict = {}

@@ -359,6 +359,58 @@ def supcon_fwd_raw(x1, x2, labels, temperature, gamma, mode, correct_grad, eps=1
     return _RawSupCon.apply(x1, x2, labels, temperature, gamma, mode, correct_grad, eps)
 
 
+class _WeightedSupCon(torch.autograd.Function):
+    """Soft positive weights (``SupConLoss3`` / ``SupConLoss4`` / ``SupConLoss2`` in-mode,
+    contrastyou/losses/contrast_loss.py:33-270) on the fp32 kernels.  ``pw``: float [pwn, pwn] with pwn = n
+    (tiled 2 x 2 like ``pos_weight.repeat(2, 2)``) or pwn = 2n; ``enable``: uint8 [2n, 2n] or None."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, z1, z2, pw, enable, temperature, in_mode):
+        _require_cuda(z1, z2, pw, enable)
+        if z1.shape != z2.shape or z1.dim() != 2:
+            raise AssertionError((tuple(z1.shape), tuple(z2.shape)))
+        n, d = z1.shape
+        N = 2 * n
+        if d > nat.MAX_D:
+            raise nat.SpclError(f"embedding width {d} > {nat.MAX_D} is not supported by this build")
+        pw = pw.to(torch.float32).contiguous()
+        if pw.dim() != 2 or pw.shape[0] != pw.shape[1] or pw.shape[0] not in (n, N):
+            raise AssertionError(tuple(pw.shape))
+        if enable is not None:
+            if tuple(enable.shape) != (N, N) or enable.dtype != torch.uint8:
+                raise TypeError("enable must be uint8 [2n, 2n]")
+            enable = enable.contiguous()
+        dev, st = z1.device, _stream(z1)
+        z = torch.cat([z1.float(), z2.float()], dim=0)               # contrast_loss.py:26
+        row_stats = torch.empty(4, N, dtype=torch.float32, device=dev)
+        partials = torch.zeros(4, dtype=torch.float32, device=dev)
+        scalars = torch.empty(4, dtype=torch.float32, device=dev)
+        inv_tau = 1.0 / float(temperature)
+        nat.call("spcl_supcon_fwd_w_f32", _ptr(z), N, d, z.stride(0), _ptr(pw), pw.shape[0], _ptr(enable), int(in_mode),
+                 inv_tau, _ptr(row_stats), N, _ptr(partials), st)
+        nat.call("spcl_supcon_finalize", _ptr(partials), N, 0, _ptr(scalars), st)
+        ctx.save_for_backward(z, pw, enable, row_stats, scalars)
+        ctx.hp = (inv_tau, int(in_mode), n, d)
+        return scalars[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        z, pw, enable, row_stats, scalars = ctx.saved_tensors
+        inv_tau, in_mode, n, d = ctx.hp
+        N = 2 * n
+        g = g.reshape(1).to(torch.float32).contiguous()
+        dz = torch.empty(N, d, dtype=torch.float32, device=z.device)
+        nat.call("spcl_supcon_bwd_w_f32", _ptr(z), N, d, z.stride(0), _ptr(pw), pw.shape[0], _ptr(enable), in_mode,
+                 inv_tau, _ptr(row_stats), N, _ptr(scalars), _ptr(g), _ptr(dz), d, _stream(z))
+        return dz[:n], dz[n:], None, None, None, None
+
+
+def supcon_weighted(z1: Tensor, z2: Tensor, pw: Tensor, enable: Optional[Tensor], temperature: float, in_mode: bool):
+    """-> 0-d loss of the soft-positive-weight SupCon family (differentiable w.r.t. z1 / z2; not w.r.t. pw)."""
+    return _WeightedSupCon.apply(z1, z2, pw, enable, float(temperature), bool(in_mode))
+
+
 class GraphRunner:
     """fwd + bwd of one loss call as ONE CUDA-graph replay, for fixed (n, d) and hyper-parameters.
 

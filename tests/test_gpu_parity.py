@@ -208,6 +208,8 @@ def test_torch_ref_matches_oracle():
     ("cfg3_dense_2x16384_d128_simclr", "soft", 8.0),
     ("cfg3_dense_2x16384_d128_slice", "soft", 10.0),
     ("cfg3_dense_2x16384_d128_slice", "none", 1e6),
+    ("cfg3_dense_2x16384_d128_slice", "hard", 10.0),      # a real threshold: ~all positives kept, near-gamma pairs exist
+    ("cfg3_dense_2x16384_d128_slice", "hard", 8.5),       # threshold inside the mass of l_ij (ratio well below 1)
 ])
 def test_cfg3_full_size_against_fp64(workload, mode, gamma):
     z1, z2, labels = make_workload(workload)
@@ -216,9 +218,12 @@ def test_cfg3_full_size_against_fp64(workload, mode, gamma):
     cls = "SupConLoss1" if mode == "none" else "SP"
     res = _run(z1, z2, cls=cls, target=lab, gamma=gamma, mode=mode, precision="bf16", validate=False)
     ref = supcon_ref64(z1, z2, lab, gamma=gamma, mode=mode)
+    # hard mode: a pair whose l_ij is within fp32 / ex2.approx rounding of gamma may land on the other side of the
+    # threshold than in fp64; each flip moves the loss by l_ij / (N c_i) ~ 1e-8 relative and one count of ~3e7
+    # positives, so the same tolerances hold -- the gradient bound below is the one that would see a real error
     assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (res["loss"], ref["loss"])
     if mode != "none":
-        assert np.isclose(res["ratio"], ref["ratio"], rtol=2e-4)
+        assert np.isclose(res["ratio"], ref["ratio"], rtol=2e-4), (res["ratio"], ref["ratio"])
     logD = res["crit"]._diag.row_stats[0, : 2 * z1.shape[0]].double()
     assert (logD - ref["logD"]).abs().max().item() < 2e-4
     ref_np = dict(dz1=ref["dz1"].cpu().numpy(), dz2=ref["dz2"].cpu().numpy())
@@ -535,3 +540,105 @@ def test_forward_raw_equals_normalize_reshape_forward(shape, mode):
     for u, w in ((a0.grad, a1.grad), (b0.grad, b1.grad)):
         assert w.shape == u.shape
         assert (u - w).abs().max().item() <= 2e-3 * u.abs().max().item()      # dZ atomics order, same formula
+
+
+# ---- oracle-based (not self-referential) checks of the f1 / f3 entry points ---------------------------------------
+@pytest.mark.parametrize("shape,mode,gamma", [((16, 128, 8, 8), "soft", 6.0), ((6, 96, 7, 5), "hard", 5.0),
+                                              ((1280, 128), "soft", 4.0), ((4, 256, 16, 16), "none", 1e6)])
+def test_forward_raw_against_the_oracle(shape, mode, gamma):
+    """``forward_raw`` (normalise + reshape + concat + bf16 pack fused into the loss) against the fp64
+    closed form: the oracle is fed the fp64-normalised rows rounded to bf16 (what the tensor-core kernels consume) and
+    its gradient rows are pulled back through the normalisation in numpy (nn.py:35-36:
+    gx = inv (g - y <y, g>), comparable.py:398-404 for the row order)."""
+    g = torch.Generator().manual_seed(11)
+    b, d = shape[0], shape[1]
+    n = int(np.prod(shape)) // d
+    inner = n // b
+    n_cls = max(2, n // 8)
+    labels = torch.randint(0, n_cls, (n,), generator=g)
+    cent = torch.randn(n_cls, d, generator=g)
+
+    def raw():
+        rows = (cent[labels] + 0.7 * torch.randn(n, d, generator=g)) * (0.5 + torch.rand(n, 1, generator=g))
+        return rows.reshape(b, inner, d).permute(0, 2, 1).reshape(shape).contiguous(), rows
+    (x1, r1), (x2, r2) = raw(), raw()
+    if mode == "none":
+        crit = spcl_b200.SupConLoss1(precision="bf16")
+    else:
+        crit = spcl_b200.SelfPacedSupConLoss(weight_update=mode, correct_grad=True, precision="bf16")
+        crit.set_gamma(gamma)
+    a, bb = x1.cuda().requires_grad_(True), x2.cuda().requires_grad_(True)
+    loss = crit.forward_raw(a, bb, target=labels.tolist())
+    loss.backward()
+
+    def unit_rows(r):                                            # fp64 normalise, then the kernels' bf16 rounding
+        r = r.double()
+        inv = 1.0 / r.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        y = r * inv
+        return y, inv, y.float().bfloat16().double()
+    y1, inv1, q1 = unit_rows(r1)
+    y2, inv2, q2 = unit_rows(r2)
+    ref = supcon_closed_form(q1.numpy(), q2.numpy(), target=labels.tolist(), gamma=gamma, mode=mode,
+                             correct_grad=(mode != "none"))
+    assert np.isclose(loss.item(), ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (loss.item(), ref["loss"])
+    if mode != "none":
+        assert np.isclose(crit.downgrade_ratio, ref["ratio"], rtol=2e-4)
+    for got, dz, y, inv in ((a.grad, ref["dz1"], y1, inv1), (bb.grad, ref["dz2"], y2, inv2)):
+        dz = torch.from_numpy(np.asarray(dz)).double()
+        gx_rows = inv * (dz - y * (y * dz).sum(1, keepdim=True))
+        want = gx_rows.reshape(b, inner, d).permute(0, 2, 1).reshape(shape)
+        got = got.double().cpu()
+        rel = (got - want).abs().max().item() / want.abs().max().item()
+        cos = (got * want).sum().item() / (got.norm().item() * want.norm().item())
+        assert rel < 3e-2 and cos > BF16_TIGHT_COS, (rel, cos)
+
+
+def test_grouped_forward_against_the_oracle():
+    """The grouped launch (K meta-label problems per kernel launch) against the fp64 closed form of
+    every problem, at the fp32 path's tolerances -- including a ragged group (different n and d per problem)."""
+    meta = acdc_meta_labels(256)
+    specs = [("partition", 256, 256, "soft", 5.0, True), ("patient", 256, 256, "hard", 3.5, False),
+             ("cycle", 200, 128, "soft", 2.0, True)]
+    crits, feats, targets, refs = [], [], [], []
+    for kind, n, d, mode, gamma, cg in specs:
+        lab = meta[kind][:n]
+        z1, z2 = make_views(lab, d, sigma=0.7, seed=3)
+        c = spcl_b200.SelfPacedSupConLoss(weight_update=mode, correct_grad=cg, precision="fp32")
+        c.set_gamma(gamma)
+        crits.append(c)
+        feats.append((z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True)))
+        targets.append(lab.tolist())
+        refs.append(supcon_closed_form(z1.numpy(), z2.numpy(), target=lab.tolist(), gamma=gamma, mode=mode,
+                                       correct_grad=cg))
+    for graph in (False, True):
+        for a, b in feats:
+            a.grad = b.grad = None
+        losses = spcl_b200.grouped_forward(crits, feats, targets, cuda_graph=graph)
+        sum(losses).backward()
+        for c, (a, b), l, ref in zip(crits, feats, losses, refs):
+            assert np.isclose(l.item(), ref["loss"], rtol=FP32_LOSS_RTOL), (graph, l.item(), ref["loss"])
+            assert np.isclose(c.downgrade_ratio, ref["ratio"], rtol=1e-4)
+            rel, cos = _grad_metrics(dict(dz1=a.grad.cpu().numpy(), dz2=b.grad.cpu().numpy()), ref)
+            assert rel < FP32_GRAD_REL, (graph, rel, cos)
+
+
+def test_gamma_zero_gives_zero_loss_like_the_reference():
+    """PScheduler's default begin_value is 0 (infonce.py:34-53): the reference then weights every positive with 0."""
+    labels = acdc_meta_labels(96)["patient"]
+    z1, z2 = make_views(labels, 64, sigma=0.7, seed=2)
+    for precision, n_rep in (("fp32", 1), ("bf16", 1)):
+        for mode in ("soft", "hard"):
+            res = _run(z1, z2, target=labels.tolist(), gamma=0.0, mode=mode, precision=precision)
+            assert res["loss"] == 0.0 and res["ratio"] == 0.0
+            assert np.abs(res["dz1"]).max() == 0.0 and np.abs(res["dz2"]).max() == 0.0
+
+
+def test_low_temperature_falls_back_to_the_fp32_kernels_under_auto():
+    """1 / T > 40 is outside the tensor-core kernels' range: precision="auto" must still compute the loss."""
+    labels = acdc_meta_labels(600)["partition"]
+    z1, z2 = make_views(labels, 64, sigma=0.7, seed=4)
+    res = _run(z1, z2, target=labels.tolist(), gamma=30.0, mode="soft", temperature=0.02, precision="auto")
+    ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=30.0, mode="soft", temperature=0.02)
+    assert np.isclose(res["loss"], ref["loss"], rtol=1e-4), (res["loss"], ref["loss"])
+    with pytest.raises(nat.SpclError):
+        _run(z1, z2, target=labels.tolist(), gamma=30.0, mode="soft", temperature=0.02, precision="bf16")
