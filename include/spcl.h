@@ -135,6 +135,16 @@ int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_t B, int64_
 int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
                         int64_t ph, int64_t pw, int64_t P, float* gx, spcl_stream_t stream);
 
+/* The same two entry points with AdaptiveMaxPool2d (pool_name="adaptive_max", contrastyou/projectors/nn.py:57-58,
+ * heads.py:96-115).  argmax: int32 [B*P][C], the flat input position h*W + w of every pooled value (first maximum in
+ * row-major window order, like torch); the backward adds g_pooled to exactly those elements of gx (zeroed by the
+ * call).  points as above (NULL = every pooled pixel). */
+int spcl_dense_rows_max_fwd(const float* x, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
+                            int64_t ph, int64_t pw, int64_t P, float eps, float* y, float* inv_norm,
+                            int32_t* argmax, spcl_stream_t stream);
+int spcl_dense_rows_max_bwd(const float* g_pooled, const int32_t* argmax, int64_t B, int64_t C, int64_t H, int64_t W,
+                            int64_t P, float* gx, spcl_stream_t stream);
+
 /* per-128-anchor label signatures used to skip tiles without positives: int32[n_pad/128][4] */
 int spcl_label_block_sig(const int32_t* labels, int64_t n_total, int64_t n_pad, int32_t* sig,
                          spcl_stream_t stream);

@@ -334,6 +334,56 @@ __global__ void __launch_bounds__(256) pool_points_bwd(const float* __restrict__
   }
 }
 
+// ---- adaptive MAX pooling (heads.py:96-115 with pool_name="adaptive_max", nn.py:57-58) -------------------------------
+// One warp per output row (image, pooled pixel | sampled point), lanes over channels.  The arg-max position of every
+// (row, channel) is kept for the backward, which routes the gradient to that input element only (first maximum in
+// row-major window order, like torch's adaptive_max_pool2d).  Not the reference's default pooling: functional, not
+// tuned (a lane walks its channel's window, so reads are strided by H * W across the warp).
+__global__ void __launch_bounds__(256) pool_max_fwd(const float* __restrict__ x, const int32_t* __restrict__ pts,
+                                                    float* __restrict__ y, float* __restrict__ inv_norm,
+                                                    int32_t* __restrict__ argmax, int64_t rows, int P, int C, int H,
+                                                    int W, int ph, int pw, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int64_t b = r / P;
+  const int q = pts != nullptr ? pts[r] : (int)(r % P);
+  if (static_cast<unsigned>(q) >= static_cast<unsigned>(ph * pw)) {
+    if (lane == 0) printf("spcl: point coordinate %d outside the %d x %d pooled grid (row %lld)\n", q, ph, pw, (long long)r);
+    __trap();
+  }
+  const int i = q / pw, j = q % pw;
+  const int hs = win_begin(i, H, ph), he = win_end(i, H, ph), ws = win_begin(j, W, pw), we = win_end(j, W, pw);
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float* xc = x + (b * C + c) * (int64_t)H * W;
+    float m = xc[(int64_t)hs * W + ws];
+    int am = hs * W + ws;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const float v = xc[(int64_t)h * W + w];
+        if (v > m || v != v) { m = v; am = h * W + w; }
+      }
+    y[r * C + c] = m;
+    argmax[r * C + c] = am;
+    ss = fmaf(m, m, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  if (lane == 0) inv_norm[r] = inv;
+  for (int c = lane; c < C; c += 32) y[r * C + c] *= inv;     // same lane wrote it
+}
+
+// gx (zeroed by the caller) += g at the arg-max element of every (row, channel); windows may overlap -> atomics
+__global__ void __launch_bounds__(256) pool_max_bwd(const float* __restrict__ gp, const int32_t* __restrict__ argmax,
+                                                    float* __restrict__ gx, int64_t rows, int P, int C, int64_t HW) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int64_t b = r / P;
+  for (int c = lane; c < C; c += 32) atomicAdd(gx + (b * C + c) * HW + argmax[r * C + c], gp[r * C + c]);
+}
+
 }  // namespace dense
 }  // namespace spcl
 
@@ -429,5 +479,35 @@ extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points,
                                                                             (int)C, (int)H, (int)W, (int)ph, (int)pw);
   }
   SPCL_LAUNCH_CHECK("spcl_dense_rows_bwd");
+  return SPCL_OK;
+}
+
+// adaptive MAX pooling variants of the two entry points above (pool_name="adaptive_max")
+extern "C" int spcl_dense_rows_max_fwd(const float* x, const int32_t* points, int64_t B, int64_t C, int64_t H,
+                                       int64_t W, int64_t ph, int64_t pw, int64_t P, float eps, float* y,
+                                       float* inv_norm, int32_t* argmax, spcl_stream_t stream) {
+  if (x == nullptr || y == nullptr || inv_norm == nullptr || argmax == nullptr || !dense_args_ok(B, C, H, W, ph, pw))
+    return SPCL_ERR_INVALID_ARG;
+  if (ph > H || pw > W) return SPCL_ERR_UNSUPPORTED;
+  if (H * W > INT_MAX) return SPCL_ERR_UNSUPPORTED;
+  if (points == nullptr) P = ph * pw;
+  if (P <= 0 || P > INT_MAX) return SPCL_ERR_INVALID_ARG;
+  const int64_t rows = B * P;
+  dense::pool_max_fwd<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, points, y, inv_norm, argmax, rows, (int)P, (int)C, (int)H, (int)W, (int)ph, (int)pw, eps);
+  SPCL_LAUNCH_CHECK("spcl_dense_rows_max_fwd");
+  return SPCL_OK;
+}
+
+extern "C" int spcl_dense_rows_max_bwd(const float* g_pooled, const int32_t* argmax, int64_t B, int64_t C, int64_t H,
+                                       int64_t W, int64_t P, float* gx, spcl_stream_t stream) {
+  if (g_pooled == nullptr || argmax == nullptr || gx == nullptr || B <= 0 || C <= 0 || H <= 0 || W <= 0 || P <= 0 ||
+      C > INT_MAX || P > INT_MAX)
+    return SPCL_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SPCL_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * B * C * H * W, s));
+  const int64_t rows = B * P;
+  dense::pool_max_bwd<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>(g_pooled, argmax, gx, rows, (int)P, (int)C, H * W);
+  SPCL_LAUNCH_CHECK("spcl_dense_rows_max_bwd");
   return SPCL_OK;
 }

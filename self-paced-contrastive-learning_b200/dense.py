@@ -67,19 +67,21 @@ class DenseProjectionTail(nn.Module):
 
     ``forward(out)`` returns all pooled pixels as rows ``[B*ph*pw, C]`` (what the loss consumes after
     comparable.py:398-404); ``forward(out, points=...)`` / ``forward(out, point_nums=5, seed=s)`` returns the
-    sampled rows of the dense hook.  Only ``pool_name="adaptive_avg"`` with ``normalize=True`` is on the hot
-    path; other settings raise."""
+    sampled rows of the dense hook.  ``pool_name``: ``"adaptive_avg"`` (the reference's default, heads.py:99; the
+    bandwidth-tuned kernels) or ``"adaptive_max"`` (nn.py:57-58).  ``normalize=False`` raises: the contrastive loss
+    asserts unit rows (contrast_loss3.py:154)."""
 
     def __init__(self, spatial_size: Sequence[int] = (16, 16), pool_name: str = "adaptive_avg", normalize: bool = True):
         super().__init__()
-        if pool_name != "adaptive_avg":
-            raise NotImplementedError("only adaptive_avg pooling is fused (the reference's default, heads.py:99)")
+        if pool_name not in ("adaptive_avg", "adaptive_max"):
+            raise NotImplementedError(f"pool_name {pool_name!r}: the dense contrast heads pool with adaptive_avg / adaptive_max")
         if not normalize:
             raise NotImplementedError("the contrastive loss asserts unit rows (contrast_loss3.py:154)")
+        self._pool = "max" if pool_name == "adaptive_max" else "avg"
         self._spatial_size: Tuple[int, int] = tuple(int(v) for v in spatial_size)
 
     def forward(self, out: Tensor, points: Optional[Tensor] = None, point_nums: Optional[int] = None,
                 seed: Optional[int] = None) -> Tensor:
         if points is None and point_nums is not None:
             points = point_coordinates(out.shape[0], *self._spatial_size, point_nums, seed)
-        return ops.dense_rows(out, self._spatial_size, points)
+        return ops.dense_rows(out, self._spatial_size, points, pool=self._pool)

@@ -559,17 +559,22 @@ class _DenseRows(torch.autograd.Function):
 
     @staticmethod
     @on_device_of(1)
-    def forward(ctx, x, points, ph, pw, eps):
+    def forward(ctx, x, points, ph, pw, eps, pool_max=False):
         _require_cuda(x, points)
         x = x.contiguous()
         B, C, H, W = x.shape
         P = ph * pw if points is None else points.shape[1]
         y = torch.empty(B * P, C, dtype=torch.float32, device=x.device)
         inv = torch.empty(B * P, dtype=torch.float32, device=x.device)
+        argmax = torch.empty(B * P, C, dtype=torch.int32, device=x.device) if pool_max else None
         if y.numel():
-            nat.call("spcl_dense_rows_fwd", _ptr(x), _ptr(points), B, C, H, W, ph, pw, P, float(eps), _ptr(y),
-                     _ptr(inv), _stream(x))
-        ctx.save_for_backward(y, inv, points)
+            if pool_max:
+                nat.call("spcl_dense_rows_max_fwd", _ptr(x), _ptr(points), B, C, H, W, ph, pw, P, float(eps), _ptr(y),
+                         _ptr(inv), _ptr(argmax), _stream(x))
+            else:
+                nat.call("spcl_dense_rows_fwd", _ptr(x), _ptr(points), B, C, H, W, ph, pw, P, float(eps), _ptr(y),
+                         _ptr(inv), _stream(x))
+        ctx.save_for_backward(y, inv, points, argmax)
         ctx.geom = (B, C, H, W, ph, pw, P)
         ctx.mark_non_differentiable(inv)
         return y, inv
@@ -577,22 +582,27 @@ class _DenseRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _g_inv):
         if gy is None:
-            return None, None, None, None, None
-        y, inv, points = ctx.saved_tensors
+            return None, None, None, None, None, None
+        y, inv, points, argmax = ctx.saved_tensors
         B, C, H, W, ph, pw, P = ctx.geom
         g_pooled = l2norm_bwd(gy.float(), y, inv, 1)            # rows layout: d(loss)/d(pooled value)
         gx = torch.empty(B, C, H, W, dtype=torch.float32, device=y.device)
         if gx.numel():
-            nat.call("spcl_dense_rows_bwd", _ptr(g_pooled), _ptr(points), B, C, H, W, ph, pw, P, _ptr(gx),
-                     _stream(y))
-        return gx, None, None, None, None
+            if argmax is not None:
+                nat.call("spcl_dense_rows_max_bwd", _ptr(g_pooled), _ptr(argmax), B, C, H, W, P, _ptr(gx), _stream(y))
+            else:
+                nat.call("spcl_dense_rows_bwd", _ptr(g_pooled), _ptr(points), B, C, H, W, ph, pw, P, _ptr(gx),
+                         _stream(y))
+        return gx, None, None, None, None, None
 
 
-def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: float = 1e-12) -> Tensor:
+def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: float = 1e-12,
+               pool: str = "avg") -> Tensor:
     """Unit-norm anchor rows from a dense projector output.
 
-    ``x``: ``[B, C, H, W]`` (any float dtype; computed in fp32).  ``spatial_size``: the adaptive-average-pool
-    target ``(ph, pw)`` (``None`` = no pooling).  ``points``: ``None`` for every pooled pixel (rows ordered
+    ``x``: ``[B, C, H, W]`` (any float dtype; computed in fp32).  ``spatial_size``: the adaptive-pool target
+    ``(ph, pw)`` (``None`` = no pooling); ``pool``: ``"avg"`` (``AdaptiveAvgPool2d``, the reference's default) or
+    ``"max"`` (``AdaptiveMaxPool2d``, ``pool_name="adaptive_max"``).  ``points``: ``None`` for every pooled pixel (rows ordered
     ``(b, i, j)``) or an integer tensor ``[B, P]`` of flat pooled coordinates ``i * pw + j`` (rows ordered
     ``(b, p)``).  Differentiable with respect to ``x``."""
     if x.dim() != 4:
@@ -614,7 +624,9 @@ def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: fl
             if points.numel() and (int(points.min()) < 0 or int(points.max()) >= ph * pw):
                 raise IndexError(f"point coordinate outside the {ph} x {pw} pooled grid")
         points = points.to(device=x.device, dtype=torch.int32).contiguous()
-    y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps))
+    if pool not in ("avg", "max"):
+        raise ValueError(f"pool must be 'avg' or 'max', got {pool!r}")
+    y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps), pool == "max")
     return y
 
 

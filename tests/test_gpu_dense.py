@@ -95,6 +95,32 @@ def test_dense_rows_points_vs_torch(B, C, H, W, ph, pw, P):
         spcl_b200.ops.dense_rows(x0, (ph, pw), torch.full((B, P), ph * pw, dtype=torch.int32))
 
 
+@pytest.mark.parametrize("B,C,H,W,ph,pw,P", [(2, 128, 56, 56, 10, 10, None), (3, 64, 28, 28, 16, 16, None),
+                                            (2, 33, 17, 19, 5, 7, None), (4, 96, 56, 56, 10, 10, 5),
+                                            (1, 8, 5, 5, 1, 1, None)])
+def test_dense_rows_adaptive_max_vs_torch(B, C, H, W, ph, pw, P):
+    """pool_name="adaptive_max" (nn.py:57-58): rows and gradients vs torch's adaptive_max_pool2d + F.normalize."""
+    gen = torch.Generator().manual_seed(B * 100 + C)
+    x0 = torch.randn(B, C, H, W, generator=gen).cuda()
+    pts = None if P is None else spcl_b200.point_coordinates(B, ph, pw, P, seed=3)
+    x = x0.clone().requires_grad_(True)
+    xr = x0.clone().requires_grad_(True)
+    rows = spcl_b200.ops.dense_rows(x, (ph, pw), pts, pool="max")
+    pooled = F.normalize(F.adaptive_max_pool2d(xr, (ph, pw)), dim=1)
+    ref = pooled.permute(0, 2, 3, 1).reshape(B, ph * pw, C)
+    if pts is not None:
+        ref = torch.gather(ref, 1, pts.cuda().long()[:, :, None].expand(-1, -1, C))
+    ref = ref.reshape(-1, C)
+    assert rows.shape == ref.shape
+    assert (rows - ref).abs().max().item() < ROW_ATOL
+    gy = torch.randn(rows.shape, generator=gen).cuda()
+    rows.backward(gy)
+    ref.backward(gy)
+    assert (x.grad - xr.grad).abs().max().item() / xr.grad.abs().max().item() < GRAD_REL
+    tail = spcl_b200.DenseProjectionTail((ph, pw), pool_name="adaptive_max")
+    assert torch.equal(tail(x0, points=pts), rows.detach())
+
+
 def test_dense_rows_zero_vector_uses_eps_like_f_normalize():
     x = torch.zeros(1, 16, 8, 8, device="cuda")
     x[0, :, 4:, :] = 1.0
@@ -214,6 +240,71 @@ def test_cfg5_encoder_step_fused_vs_reference_loss():
         # identical weights and inputs: the two arms may only drift by fp32 rounding through the optimiser
         assert vals["fused"][0] == pytest.approx(vals["ref"][0], rel=1e-3), (step, vals)
         assert vals["fused"][1] == pytest.approx(vals["ref"][1], rel=2e-2), (step, vals)
+
+
+def _ref_parts():
+    from baseline import ref_loader
+    if not ref_loader.available():
+        pytest.skip("baseline/_ref is not installed (tools/install_ref.sh)")
+    return ref_loader.unet_module().UNet, ref_loader.heads_module(), ref_loader.loss_module()
+
+
+def test_cfg5_step_on_the_reference_unet_matches_the_reference_loss():
+    """cfg5 with the reference's OWN modules on both sides of the loss: UNet(..., until="Conv5") and
+    ProjectionHead(256, 256, 256, "mlp") from baseline/_ref; the only difference between the arms is the loss module
+    (unmodified contrast_loss3.SelfPacedSupConLoss vs the fused one)."""
+    UNet, heads, ref_loss = _ref_parts()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n = 12
+    labels = acdc_meta_labels(n)["partition"].tolist()
+
+    def make():
+        torch.manual_seed(0)
+        enc = UNet(input_dim=1, num_classes=4, max_channel=256).cuda()
+        head = heads.ProjectionHead(input_dim=256, hidden_dim=256, output_dim=256, head_type="mlp", normalize=True).cuda()
+        params = [q for q in list(enc.parameters()) + list(head.parameters())]
+        return enc, head, torch.optim.SGD(params, lr=1e-2, momentum=0.9)
+
+    arms = {"fused": make(), "ref": make()}
+    crits = {"fused": spcl_b200.SelfPacedSupConLoss(weight_update="soft", correct_grad=True),
+             "ref": ref_loss.SelfPacedSupConLoss(weight_update="soft", correct_grad=True)}
+    for c in crits.values():
+        c.set_gamma(8.0)
+    gen = torch.Generator().manual_seed(5)
+    for step in range(3):
+        x = torch.randn(2 * n, 1, 96, 96, generator=gen).cuda()
+        vals = {}
+        for name, (enc, head, opt) in arms.items():
+            opt.zero_grad(set_to_none=True)
+            za, zb = torch.chunk(head(enc(x, until="Conv5")), 2)
+            loss = crits[name](za, zb, target=labels)
+            loss.backward()
+            gn = torch.sqrt(sum((q.grad.double() ** 2).sum() for q in head.parameters()))
+            opt.step()
+            vals[name] = (loss.item(), gn.item(), crits[name].downgrade_ratio)
+        assert vals["fused"][0] == pytest.approx(vals["ref"][0], rel=1e-3), (step, vals)
+        assert vals["fused"][1] == pytest.approx(vals["ref"][1], rel=2e-2), (step, vals)
+        assert vals["fused"][2] == pytest.approx(vals["ref"][2], rel=1e-3), (step, vals)
+
+
+@pytest.mark.parametrize("pool_name", ["adaptive_avg", "adaptive_max"])
+def test_decoder_step_on_the_reference_unet(pool_name):
+    """Decoder-stage step (main_pretrain_decoder.py:42-76 + infonce.py:198-241): reference UNet up to Up_conv3 with the
+    encoder frozen, the reference's DenseProjectionHead + region_extractor + SupConLoss1 on one side, this repo's head
+    tail (pool + normalise + point gather in one kernel) + fused loss on the other; same weights, same sampled points."""
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location("decoder_step", pathlib.Path(__file__).resolve().parent.parent / "tools" / "decoder_step.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.measure(batch=6, steps=3, warmup=0, image=96, pool_name=pool_name, tf32=False)
+    if "reference" not in out:
+        pytest.skip("baseline/_ref is not installed (tools/install_ref.sh)")
+    for lf, lr in zip(out["fused"]["losses"], out["reference"]["losses"]):
+        assert lf == pytest.approx(lr, rel=1e-4), out
+    for gf, gr in zip(out["fused"]["grad_norms"], out["reference"]["grad_norms"]):
+        assert gf == pytest.approx(gr, rel=5e-3), out
 
 
 # ---- grouped launch (SURVEY 8 f3, cfg2): K problems per launch == K separate calls -----------------------------

@@ -289,9 +289,10 @@ def test_group_abi_validates_arguments_without_touching_the_gpu():
 def test_dense_tail_rejects_what_is_not_on_the_hot_path():
     import spcl_b200
     with pytest.raises(NotImplementedError):
-        spcl_b200.DenseProjectionTail((16, 16), pool_name="adaptive_max")
+        spcl_b200.DenseProjectionTail((16, 16), pool_name="identical")
     with pytest.raises(NotImplementedError):
         spcl_b200.DenseProjectionTail((16, 16), normalize=False)
+    assert spcl_b200.DenseProjectionTail((16, 16), pool_name="adaptive_max")._pool == "max"
     assert spcl_b200.DenseProjectionTail((10, 10))._spatial_size == (10, 10)
 
 
