@@ -659,7 +659,9 @@ def main():
             dense_fe = {"workload": "DenseProjectionHead tail: 32 x 128 x 224 x 224 -> 32 x 32 pooled, normalised rows",
                         "bound": "hbm", "peak": r["peak_gbs"], "unit": "GB/s", "fwd_ms": c["fwd_ms"], "bwd_ms": c["bwd_ms"],
                         "fwd_achieved": c["fwd_gbs"], "fwd_frac": c["fwd_frac"], "bwd_achieved": c["bwd_gbs"],
-                        "bwd_frac": c["bwd_frac"], "l2": c["l2"]}
+                        "bwd_frac": c["bwd_frac"], "l2": c["l2"], "fwd_queued_ms": c["fwd_queued_ms"],
+                        "bwd_queued_ms": c["bwd_queued_ms"], "fwd_queued_frac": c["fwd_queued_frac"],
+                        "bwd_queued_frac": c["bwd_queued_frac"], "queued": c["queued"]}
         except Exception as e:
             dense_fe = {"error": f"{type(e).__name__}: {e}"}
 

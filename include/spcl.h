@@ -134,6 +134,12 @@ int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_t B, int64_
  * is fully written (zeros outside the sampled windows). */
 int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
                         int64_t ph, int64_t pw, int64_t P, float* gx, spcl_stream_t stream);
+/* The same backward with F.normalize's backward folded into the load phase: gy = gradient with respect to the unit
+ * rows y (both float [B*P][C]), inv_norm as written by spcl_dense_rows_fwd; no intermediate g_pooled tensor and no
+ * separate spcl_l2norm_bwd launch. */
+int spcl_dense_rows_bwd_fused(const float* gy, const float* y, const float* inv_norm, const int32_t* points, int64_t B,
+                              int64_t C, int64_t H, int64_t W, int64_t ph, int64_t pw, int64_t P, float* gx,
+                              spcl_stream_t stream);
 
 /* The same two entry points with AdaptiveMaxPool2d (pool_name="adaptive_max", contrastyou/projectors/nn.py:57-58,
  * heads.py:96-115).  argmax: int32 [B*P][C], the flat input position h*W + w of every pooled value (first maximum in

@@ -35,6 +35,7 @@ SIGNATURES = {
     "spcl_supcon_raw_bwd": [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr],
     "spcl_dense_rows_fwd": [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _ptr, _ptr, _ptr],
     "spcl_dense_rows_bwd": [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
+    "spcl_dense_rows_bwd_fused": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
     "spcl_dense_rows_max_fwd": [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _ptr, _ptr, _ptr, _ptr],
     "spcl_dense_rows_max_bwd": [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
     "spcl_supcon_fwd_bf16": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _i64, _f32, _f32, _c.c_int, _ptr, _ptr,

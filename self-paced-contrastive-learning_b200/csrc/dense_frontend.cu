@@ -204,8 +204,9 @@ __global__ void __launch_bounds__(256) pool_rows_fwd_tma(const float* __restrict
 // dynamic shared memory: C * (pw + 1) floats
 // EXACT: H % ph == 0 and W % pw == 0 -- every pixel lies in exactly one window of constant size
 template <bool VEC4, bool EXACT>
-__global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, float* __restrict__ gx, int C,
-                                                     int H, int W, int ph, int pw) {
+__global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ gp, const float* __restrict__ yrows,
+                                                     const float* __restrict__ inv_norm, float* __restrict__ gx,
+                                                     int C, int H, int W, int ph, int pw) {
   extern __shared__ float G[];                            // [C][pw + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -222,9 +223,28 @@ __global__ void __launch_bounds__(256) pool_rows_bwd(const float* __restrict__ g
   for (int j = warp; j < pw; j += 8) {
     const int wlen = EXACT ? W / pw : win_end(j, W, pw) - win_begin(j, W, pw);
     const float r0 = 1.f / (float)(ilen[0] * wlen), r1 = ni > 1 ? 1.f / (float)(ilen[1] * wlen) : 0.f;
-    const float* g0 = gp + (((int64_t)b * ph + irow[0]) * pw + j) * C;
-    const float* g1 = gp + (((int64_t)b * ph + irow[ni > 1 ? 1 : 0]) * pw + j) * C;
-    if (EXACT) {
+    const int64_t row0 = ((int64_t)b * ph + irow[0]) * pw + j, row1 = ((int64_t)b * ph + irow[ni > 1 ? 1 : 0]) * pw + j;
+    const float* g0 = gp + row0 * C;
+    const float* g1 = gp + row1 * C;
+    if (yrows != nullptr) {
+      // gp holds the gradient of the UNIT rows: the normalise backward g = inv (gy - y <y, gy>) (nn.py:35-36) is folded
+      // into this load phase -- the rows are L2 resident, so the separate l2norm launch and its 2 x 4 B P C bytes go away
+      const float* y0 = yrows + row0 * C;
+      const float* y1 = yrows + row1 * C;
+      float d0 = 0.f, d1 = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        d0 = fmaf(__ldg(g0 + c), __ldg(y0 + c), d0);
+        if (!EXACT) d1 = fmaf(__ldg(g1 + c), __ldg(y1 + c), d1);
+      }
+      d0 = warp_sum(d0);
+      if (!EXACT) d1 = warp_sum(d1);
+      const float s0 = r0 * __ldg(inv_norm + row0), s1 = r1 * __ldg(inv_norm + row1);
+      for (int c = lane; c < C; c += 32) {
+        float v = (__ldg(g0 + c) - __ldg(y0 + c) * d0) * s0;
+        if (!EXACT) v = fmaf(__ldg(g1 + c) - __ldg(y1 + c) * d1, s1, v);
+        G[c * stride + j] = v;
+      }
+    } else if (EXACT) {
       for (int c = lane; c < C; c += 32) G[c * stride + j] = __ldg(g0 + c) * r0;
     } else {
       for (int c = lane; c < C; c += 32) G[c * stride + j] = fmaf(__ldg(g1 + c), r1, __ldg(g0 + c) * r0);
@@ -309,7 +329,9 @@ __global__ void __launch_bounds__(256) pool_points_fwd(const float* __restrict__
 
 // scatter of the pooled-value gradient rows back into gx (zeroed by the caller); windows of different points
 // can share border pixels when H % ph != 0, hence atomics (a few thousand of them).
-__global__ void __launch_bounds__(256) pool_points_bwd(const float* __restrict__ gp, const int32_t* __restrict__ pts,
+__global__ void __launch_bounds__(256) pool_points_bwd(const float* __restrict__ gp, const float* __restrict__ yrows,
+                                                       const float* __restrict__ inv_norm,
+                                                       const int32_t* __restrict__ pts,
                                                        float* __restrict__ gx, int64_t rows, int P, int C, int H,
                                                        int W, int ph, int pw) {
   const int lane = threadIdx.x & 31;
@@ -325,9 +347,15 @@ __global__ void __launch_bounds__(256) pool_points_bwd(const float* __restrict__
   }
   const int i = q / pw, j = q % pw;
   const int hs = win_begin(i, H, ph), he = win_end(i, H, ph), ws = win_begin(j, W, pw), we = win_end(j, W, pw);
-  const float inv_area = 1.f / (float)((he - hs) * (we - ws));
+  float inv_area = 1.f / (float)((he - hs) * (we - ws));
+  float dot = 0.f;
+  if (yrows != nullptr) {                        // normalise backward folded in (see pool_rows_bwd)
+    for (int c = lane; c < C; c += 32) dot = fmaf(gp[r * C + c], yrows[r * C + c], dot);
+    dot = warp_sum(dot);
+    inv_area *= inv_norm[r];
+  }
   for (int c = lane; c < C; c += 32) {
-    const float g = gp[r * C + c] * inv_area;
+    const float g = (gp[r * C + c] - (yrows != nullptr ? yrows[r * C + c] * dot : 0.f)) * inv_area;
     float* xc = gx + (b * C + c) * (int64_t)H * W;
     for (int h = hs; h < he; ++h)
       for (int w = ws; w < we; ++w) atomicAdd(xc + (int64_t)h * W + w, g);
@@ -454,8 +482,26 @@ extern "C" int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_
   return SPCL_OK;
 }
 
+static int dense_rows_bwd_impl(const float* g_pooled, const float* yrows, const float* inv_norm, const int32_t* points,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int64_t ph, int64_t pw, int64_t P,
+                               float* gx, spcl_stream_t stream);
+
 extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points, int64_t B, int64_t C, int64_t H,
                                    int64_t W, int64_t ph, int64_t pw, int64_t P, float* gx, spcl_stream_t stream) {
+  return dense_rows_bwd_impl(g_pooled, nullptr, nullptr, points, B, C, H, W, ph, pw, P, gx, stream);
+}
+
+// the same with the normalise backward folded in: gy = gradient of the UNIT rows y, inv_norm as written by the forward
+extern "C" int spcl_dense_rows_bwd_fused(const float* gy, const float* y, const float* inv_norm, const int32_t* points,
+                                         int64_t B, int64_t C, int64_t H, int64_t W, int64_t ph, int64_t pw, int64_t P,
+                                         float* gx, spcl_stream_t stream) {
+  if (y == nullptr || inv_norm == nullptr) return SPCL_ERR_INVALID_ARG;
+  return dense_rows_bwd_impl(gy, y, inv_norm, points, B, C, H, W, ph, pw, P, gx, stream);
+}
+
+static int dense_rows_bwd_impl(const float* g_pooled, const float* yrows, const float* inv_norm, const int32_t* points,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int64_t ph, int64_t pw, int64_t P,
+                               float* gx, spcl_stream_t stream) {
   if (g_pooled == nullptr || gx == nullptr || !dense_args_ok(B, C, H, W, ph, pw)) return SPCL_ERR_INVALID_ARG;
   if (ph > H || pw > W) return SPCL_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -470,13 +516,13 @@ extern "C" int spcl_dense_rows_bwd(const float* g_pooled, const int32_t* points,
                      : (exact ? dense::pool_rows_bwd<false, true> : dense::pool_rows_bwd<false, false>);
     if (smem > 48 * 1024)
       SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
+    kern<<<(unsigned)(B * H), 256, smem, s>>>(g_pooled, yrows, inv_norm, gx, (int)C, (int)H, (int)W, (int)ph, (int)pw);
   } else {
     if (P <= 0 || P > INT_MAX) return SPCL_ERR_INVALID_ARG;
     SPCL_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * B * C * H * W, s));
     const int64_t rows = B * P;
-    dense::pool_points_bwd<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>(g_pooled, points, gx, rows, (int)P,
-                                                                            (int)C, (int)H, (int)W, (int)ph, (int)pw);
+    dense::pool_points_bwd<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>(g_pooled, yrows, inv_norm, points, gx, rows,
+                                                                            (int)P, (int)C, (int)H, (int)W, (int)ph, (int)pw);
   }
   SPCL_LAUNCH_CHECK("spcl_dense_rows_bwd");
   return SPCL_OK;

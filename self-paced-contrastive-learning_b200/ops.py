@@ -585,14 +585,16 @@ class _DenseRows(torch.autograd.Function):
             return None, None, None, None, None, None
         y, inv, points, argmax = ctx.saved_tensors
         B, C, H, W, ph, pw, P = ctx.geom
-        g_pooled = l2norm_bwd(gy.float(), y, inv, 1)            # rows layout: d(loss)/d(pooled value)
         gx = torch.empty(B, C, H, W, dtype=torch.float32, device=y.device)
         if gx.numel():
+            gy = gy.float().contiguous()
             if argmax is not None:
+                g_pooled = l2norm_bwd._init_fn(gy, y, inv, 1)       # rows layout: d(loss)/d(pooled value)
                 nat.call("spcl_dense_rows_max_bwd", _ptr(g_pooled), _ptr(argmax), B, C, H, W, P, _ptr(gx), _stream(y))
             else:
-                nat.call("spcl_dense_rows_bwd", _ptr(g_pooled), _ptr(points), B, C, H, W, ph, pw, P, _ptr(gx),
-                         _stream(y))
+                # the normalise backward is folded into the pooling backward's load phase (one launch, no g_pooled)
+                nat.call("spcl_dense_rows_bwd_fused", _ptr(gy), _ptr(y), _ptr(inv), _ptr(points), B, C, H, W, ph, pw, P,
+                         _ptr(gx), _stream(y))
         return gx, None, None, None, None, None
 
 

@@ -28,6 +28,8 @@ PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROO
 
 
 def timed(fn, reps=20, flush=None):
+    """Median device time between two events with the launch queue primed by a ~0.25 ms spin kernel (the host has
+    enqueued fn() before the GPU reaches the start event: no Python / launch latency inside the interval)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -35,6 +37,7 @@ def timed(fn, reps=20, flush=None):
     for _ in range(reps):
         if flush is not None:
             flush.zero_()
+        torch.cuda._sleep(500_000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
