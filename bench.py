@@ -455,10 +455,13 @@ def main():
     for _ in range(args.warmup):
         a.grad = b.grad = None
         fwd_bwd(a, b, lab)
-    sync_all()
+    # everything host-side that differs in duration from rank to rank (NVML start-up, event creation) happens BEFORE the
+    # barrier: a rank that enters the first timed step late makes every other rank wait inside its timed region
+    # (r02s on 8 GPUs: first step 7-18 ms against 5.75 ms for the following ones)
     sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler.start()
+    sync_all()
     for s, e in evs:
         a.grad = b.grad = None
         flush.zero_()
@@ -482,7 +485,7 @@ def main():
         parity = sharded_parity(dist, dev, a, b, lab, world, rank, loss_val, last["scalars"].tolist())
         gathered = [None] * world
         dist.all_gather_object(gathered, {"rank": rank, "ms_per_step_local": sum(s.elapsed_time(e) for s, e in evs) / args.steps,
-                                          **clocks})
+                                          "step_ms": [round(s.elapsed_time(e), 3) for s, e in evs[:12]], **clocks})
         per_rank = gathered
         base = torch.zeros(2, dtype=torch.float64, device=dev)
         if rank == 0 and not args.quick:

@@ -521,6 +521,98 @@ __device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int jd
   }
 }
 
+// sp pass, tile whose 128 x 128 pairs are ALL positives (row block and column tile carry one and the same label, no
+// diagonal, no tail): no label reads, no per-element predicates, packed arithmetic.  cfg3 with slice labels (1024
+// pixels per label) consists of such tiles only, 1/16 of the grid.  MODE as p.mode.
+template <int MODE>
+__device__ __forceinline__ void sp_chunk_allpos(const uint32_t (&v)[32], const Params& p, float logD, float& wl,
+                                                float& wp) {
+  if (MODE == SPCL_MODE_NONE) {                       // wl = sum P <z_i, z_j>
+    uint64_t a = 0ull;
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) a = add_f32x2(a, pack_u32x2(v[e], v[e + 1]));
+    float lo, hi;
+    unpack_f32x2(a, lo, hi);
+    wl += lo + hi;
+    return;
+  }
+  const uint64_t it2 = pack_f32x2(p.inv_tau, p.inv_tau), nld2 = pack_f32x2(-logD, -logD);
+  const uint64_t ig2 = pack_f32x2(p.inv_gamma, p.inv_gamma), one2 = pack_f32x2(1.f, 1.f);
+  uint64_t wl2 = 0ull, wp2 = 0ull;
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const uint64_t nl2 = fma_f32x2(pack_u32x2(v[e], v[e + 1]), it2, nld2);      // -l = S - logD = LLH
+    float w0, w1;
+    if (MODE == SPCL_MODE_SOFT) {
+      unpack_f32x2(fma_f32x2(nl2, ig2, one2), w0, w1);                          // 1 - l / gamma
+      w0 = fmaxf(w0, 0.f);
+      w1 = fmaxf(w1, 0.f);
+    } else {
+      float n0, n1;
+      unpack_f32x2(nl2, n0, n1);
+      w0 = (-n0 <= p.gamma) ? 1.f : 0.f;
+      w1 = (-n1 <= p.gamma) ? 1.f : 0.f;
+    }
+    const uint64_t w2 = pack_f32x2(w0, w1);
+    wl2 = fma_f32x2(w2, nl2, wl2);                                              // sum P W LLH
+    wp2 = add_f32x2(wp2, w2);
+  }
+  float a0, a1, b0, b1;
+  unpack_f32x2(wl2, a0, a1);
+  unpack_f32x2(wp2, b0, b1);
+  wl += a0 + a1;
+  wp += b0 + b1;
+}
+
+// backward, all-positive tile (see sp_chunk_allpos): T = E (u_i + u_j) - (W_ij / c_i + W_ji / c_j) with
+// W_ij = w(logD_i - S), W_ji = w(logD_j - S); column statistics come in float4 groups from the slot.
+template <int MODE>
+__device__ __forceinline__ void bwd_chunk_allpos(const uint32_t (&v)[32], const float* logD_s, const float* invc_s,
+                                                 const float* u_s, const ExpK& k, const Params& p, float logD_i,
+                                                 float invc_i, uint64_t uiui, uint32_t (&pk)[16]) {
+  const uint64_t it2 = pack_f32x2(p.inv_tau, p.inv_tau), nldi2 = pack_f32x2(-logD_i, -logD_i);
+  const uint64_t ig2 = pack_f32x2(p.inv_gamma, p.inv_gamma), one2 = pack_f32x2(1.f, 1.f);
+  const uint64_t ici2 = pack_f32x2(invc_i, invc_i);
+  auto weight2 = [&](uint64_t nl2) -> uint64_t {          // nl2 = -(l) for two pairs
+    float w0, w1;
+    if (MODE == SPCL_MODE_SOFT) {
+      unpack_f32x2(fma_f32x2(nl2, ig2, one2), w0, w1);
+      w0 = fmaxf(w0, 0.f);
+      w1 = fmaxf(w1, 0.f);
+    } else if (MODE == SPCL_MODE_HARD) {
+      float n0, n1;
+      unpack_f32x2(nl2, n0, n1);
+      w0 = (-n0 <= p.gamma) ? 1.f : 0.f;
+      w1 = (-n1 <= p.gamma) ? 1.f : 0.f;
+    } else {
+      w0 = w1 = 1.f;
+    }
+    return pack_f32x2(w0, w1);
+  };
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    const float4 uj = *reinterpret_cast<const float4*>(u_s + e);
+    const float4 ldj = *reinterpret_cast<const float4*>(logD_s + e);
+    const float4 icj = *reinterpret_cast<const float4*>(invc_s + e);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t d2 = pack_u32x2(v[e + 2 * h], v[e + 2 * h + 1]);
+      const uint64_t ex = use_poly((e >> 1) + h, SPCL_BWD_POLY_PAIRS) ? ex2_poly2<3>(d2, k) : ex2_mufu2(d2, k);
+      const uint64_t uj2 = h ? pack_f32x2(uj.z, uj.w) : pack_f32x2(uj.x, uj.y);
+      const uint64_t nldj2 = h ? pack_f32x2(-ldj.z, -ldj.w) : pack_f32x2(-ldj.x, -ldj.y);
+      const uint64_t icj2 = h ? pack_f32x2(icj.z, icj.w) : pack_f32x2(icj.x, icj.y);
+      const uint64_t wi2 = weight2(fma_f32x2(d2, it2, nldi2));
+      const uint64_t wj2 = weight2(fma_f32x2(d2, it2, nldj2));
+      const uint64_t pen2 = fma_f32x2(wi2, ici2, mul_f32x2(wj2, icj2));
+      // T = E (u_i + u_j) - pen
+      const uint64_t t2 = fma_f32x2(ex, add_f32x2(uj2, uiui), fma_f32x2(pen2, pack_f32x2(-1.f, -1.f), 0ull));
+      float t0, t1;
+      unpack_f32x2(t2, t0, t1);
+      pk[(e >> 1) + h] = pack_bf16x2(t0, t1);
+    }
+  }
+}
+
 // fast: T = E * (u_i + u_j), packed to bf16 pairs
 __device__ __forceinline__ void bwd_chunk_fast(const uint32_t (&v)[32], const float* u_s, const ExpK& k, uint64_t uiui,
                                                uint32_t (&pk)[16]) {
@@ -1020,6 +1112,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           tc_fence_after();
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
+          // every pair of the tile a positive?  (one label on both sides, off the diagonal block, no tail columns)
+          const int4 csig = sigt[t];
+          const bool allpos = rsig.x == rsig.y && csig.x == csig.y && csig.x == rsig.x && t * TILE != gi0 &&
+                              jmax == TILE && !(p.dbg & 8192);
           uint32_t va[32], vb[32];
           tmem_ld_32x32b_x32(taddr, va);
           tmem_wait_ld();
@@ -1028,9 +1124,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
             uint32_t(&cur)[32] = (ch & 1) ? vb : va;
             uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
             if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
-            sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
+            if (!allpos) sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
+            else if (p.mode == SPCL_MODE_SOFT) sp_chunk_allpos<SPCL_MODE_SOFT>(cur, p, logD, s0, s1);
+            else if (p.mode == SPCL_MODE_HARD) sp_chunk_allpos<SPCL_MODE_HARD>(cur, p, logD, s0, s1);
+            else sp_chunk_allpos<SPCL_MODE_NONE>(cur, p, logD, s0, s1);
             if (ch < 3) tmem_wait_ld();
           }
+          if (allpos) cnt += static_cast<float>(TILE);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -1269,10 +1369,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
     const uint32_t ct128 = static_cast<uint32_t>(p.CT128);
     const uint32_t tail_jb = (p.N % TILE) ? ct128 - 1u : 0xffffffffu;
     uint32_t row_jb = 0;
+    uint32_t apmask = 0;                                 // tiles of the group whose pairs are ALL positives
     auto slow_mask = [&](uint32_t grp) -> uint32_t {
       const uint32_t t = (grp << 5) + static_cast<uint32_t>(lane);
-      bool slow = true;
-      if (t < ct128) slow = t == row_jb || t == tail_jb || sig_overlap(rsig, p.sig[t]);
+      bool slow = true, ap = false;
+      if (t < ct128) {
+        const int4 cs = p.sig[t];
+        const bool edge = t == row_jb || t == tail_jb;
+        slow = edge || sig_overlap(rsig, cs);
+        ap = !edge && rsig.x == rsig.y && cs.x == cs.y && cs.x == rsig.x && !(p.dbg & 8192);
+      }
+      apmask = __ballot_sync(kFullMask, ap);
       return __ballot_sync(kFullMask, slow);
     };
     uint32_t mask = 0, mask_grp = 0xffffffffu;
@@ -1299,6 +1406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           mask = slow_mask(mask_grp);
         }
         const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
+        const bool allpos = ((apmask >> (c.t & 31)) & 1u) != 0u;
         if (lane == 0) {
           mbar_wait(&bar->full[slot], ph);
           mbar_wait(&bar->s_full[buf], bph);
@@ -1332,6 +1440,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
 #else
             bwd_chunk_fast(cur, u_s + ch * 32, ek, uiui, pk);
 #endif
+          } else if (allpos && row_ok) {
+            if (p.mode == SPCL_MODE_SOFT)
+              bwd_chunk_allpos<SPCL_MODE_SOFT>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
+            else if (p.mode == SPCL_MODE_HARD)
+              bwd_chunk_allpos<SPCL_MODE_HARD>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
+            else
+              bwd_chunk_allpos<SPCL_MODE_NONE>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
           } else if (p.mode == SPCL_MODE_SOFT) {
             bwd_chunk_slow<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
                                            u_i, pk);

@@ -642,3 +642,24 @@ def test_low_temperature_falls_back_to_the_fp32_kernels_under_auto():
     assert np.isclose(res["loss"], ref["loss"], rtol=1e-4), (res["loss"], ref["loss"])
     with pytest.raises(nat.SpclError):
         _run(z1, z2, target=labels.tolist(), gamma=30.0, mode="soft", temperature=0.02, precision="bf16")
+
+
+@pytest.mark.parametrize("mode,gamma,cg", [("none", 1e6, False), ("soft", 6.0, True), ("hard", 5.5, False)])
+def test_all_positive_tiles_against_the_oracle(mode, gamma, cg):
+    """Label runs of 256 anchors: every 128 x 128 tile is either all-positive or all-negative, so the sp pass and the
+    backward take their packed all-positive paths (what cfg3's slice labels run at full size); a second labelling with
+    runs of 96 mixes them with the generic per-pair path inside one problem.  fp64 oracle on the bf16-rounded operands."""
+    for run in (256, 96):
+        n, d = 1024, 128
+        labels = (torch.arange(n) // run)
+        z1, z2 = make_views(labels, d, sigma=0.7, seed=9)
+        z1, z2 = z1.bfloat16().float(), z2.bfloat16().float()
+        cls = "SupConLoss1" if mode == "none" else "SP"
+        res = _run(z1, z2, cls=cls, target=labels.int().numpy(), gamma=gamma, mode=mode, correct_grad=cg,
+                   precision="bf16", validate=False)
+        ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=gamma, mode=mode, correct_grad=cg)
+        assert np.isclose(res["loss"], ref["loss"], rtol=BF16_TIGHT_LOSS_RTOL), (run, res["loss"], ref["loss"])
+        if mode != "none":
+            assert np.isclose(res["ratio"], ref["ratio"], rtol=3e-4), (run, res["ratio"], ref["ratio"])
+        rel, cos = _grad_metrics(res, ref)
+        assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (run, rel, cos)
