@@ -124,7 +124,8 @@ int spcl_supcon_raw_bwd(const float* dz, int64_t lddz, const float* x1, const fl
  *   points == NULL: every pooled pixel, P = ph*pw, row (b*ph + i)*pw + j.
  *   points != NULL: int32 [B*P], points[b*P + p] = i*pw + j in the pooled grid (0 <= value < ph*pw, checked by the
  *                   caller); only those windows are read.  Row b*P + p.
- * y: float [B*P][C] unit rows, inv_norm: float [B*P] = 1 / max(||pooled||, eps).  ph <= H and pw <= W
+ * y: float [B*P][C] unit rows, inv_norm: float [B*P] = 1 / max(||pooled||, eps); eps < 0 skips the normalisation
+ * (y = the pooled rows, inv_norm = 1: DenseProjectionHead with its last 1x1 conv moved behind the pooling).  ph <= H and pw <= W
  * (SPCL_ERR_UNSUPPORTED otherwise; the reference only pools down). */
 int spcl_dense_rows_fwd(const float* x, const int32_t* points, int64_t B, int64_t C, int64_t H, int64_t W,
                         int64_t ph, int64_t pw, int64_t P, float eps, float* y, float* inv_norm,

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, MINB) pool_rows_fwd(const float* __restri
     float ss = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = pooled[c * (pw + 1) + j]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
-    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    const float inv = eps < 0.f ? 1.f : 1.f / fmaxf(sqrtf(ss), eps);      // eps < 0: pooled rows, not normalised
     const int64_t row = ((int64_t)b * ph + i) * pw + j;
     if (lane == 0) inv_norm[row] = inv;
     for (int c = lane; c < C; c += 32) y[row * C + c] = pooled[c * (pw + 1) + j] * inv;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) pool_rows_fwd_tma(const float* __restrict
     float ss = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = pooled[c * (pw + 1) + j]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
-    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    const float inv = eps < 0.f ? 1.f : 1.f / fmaxf(sqrtf(ss), eps);      // eps < 0: pooled rows, not normalised
     const int64_t row = ((int64_t)b * ph + i) * pw + j;
     if (lane == 0) inv_norm[row] = inv;
     for (int c = lane; c < C; c += 32) y[row * C + c] = pooled[c * (pw + 1) + j] * inv;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) pool_points_fwd(const float* __restrict__
     ss = fmaf(s, s, ss);
   }
   ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  const float inv = eps < 0.f ? 1.f : 1.f / fmaxf(sqrtf(ss), eps);        // eps < 0: pooled rows, not normalised
   if (lane == 0) inv_norm[r] = inv;
   for (int c = lane; c < C; c += 32) y[r * C + c] *= inv;     // same lane wrote it
 }
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256) pool_max_fwd(const float* __restrict__ x,
     ss = fmaf(m, m, ss);
   }
   ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  const float inv = eps < 0.f ? 1.f : 1.f / fmaxf(sqrtf(ss), eps);        // eps < 0: pooled rows, not normalised
   if (lane == 0) inv_norm[r] = inv;
   for (int c = lane; c < C; c += 32) y[r * C + c] *= inv;     // same lane wrote it
 }

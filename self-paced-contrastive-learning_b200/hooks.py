@@ -190,13 +190,33 @@ class DenseProjectionHead(nn.Module):
 
     def rows(self, features, points: Optional[Tensor] = None, point_nums: Optional[int] = None,
              seed: Optional[int] = None) -> Tensor:
-        return self._tail(self._projector(features), points=points, point_nums=point_nums, seed=seed)
+        """Unit anchor rows ``[B * P, C]`` (all pooled pixels, or the sampled ones).
+
+        With average pooling the LAST 1x1 convolution is moved behind the pooling: both are linear, so
+        ``pool(W h + b) == W pool(h) + b`` exactly (rounding aside), and the convolution then runs on ``ph * pw`` (or
+        only the ``P`` sampled) positions per image instead of ``H * W`` -- 125x fewer for the dense hook's 10 x 10
+        grid on a 112 x 112 map, 2500x with 5 sampled points -- and the full-resolution ``[B, C, H, W]`` projector
+        output never exists.  Order: hidden layers at full resolution -> pool (+ gather) kernel -> ``F.linear`` on the
+        rows -> normalise kernel.  Max pooling does not commute with the convolution and keeps the reference's order
+        (``commute_pooling=False`` forces that order for average pooling too: A/B and parity tests)."""
+        if points is None and point_nums is not None:
+            points = point_coordinates(features.shape[0], *self._spatial_size, point_nums, seed)
+        last = self._projector[-1]
+        if self.commute_pooling and self._tail._pool == "avg":
+            hidden = self._projector[:-1](features) if len(self._projector) > 1 else features
+            pooled = ops.dense_rows(hidden, self._spatial_size, points, normalize=False)
+            z = nn.functional.linear(pooled, last.weight.flatten(1), last.bias)
+            return ops.l2norm_fwd(z, 1, 1e-12)[0]
+        return self._tail(self._projector(features), points=points)
+
+    #: average pooling: run the last 1x1 convolution on the pooled rows (see ``rows``)
+    commute_pooling = True
 
     def forward(self, features):
-        out = self._projector(features)
-        b, c = out.shape[:2]
+        b = features.shape[0]
         ph, pw = self._spatial_size
-        return self._tail(out).reshape(b, ph, pw, c).permute(0, 3, 1, 2)
+        rows = self.rows(features)
+        return rows.reshape(b, ph, pw, rows.shape[1]).permute(0, 3, 1, 2)
 
 
 # --------------------------------------------------------------------------------------------------

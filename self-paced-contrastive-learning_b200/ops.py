@@ -576,6 +576,7 @@ class _DenseRows(torch.autograd.Function):
                          _ptr(inv), _stream(x))
         ctx.save_for_backward(y, inv, points, argmax)
         ctx.geom = (B, C, H, W, ph, pw, P)
+        ctx.normalized = eps >= 0
         ctx.mark_non_differentiable(inv)
         return y, inv
 
@@ -589,8 +590,10 @@ class _DenseRows(torch.autograd.Function):
         if gx.numel():
             gy = gy.float().contiguous()
             if argmax is not None:
-                g_pooled = l2norm_bwd._init_fn(gy, y, inv, 1)       # rows layout: d(loss)/d(pooled value)
+                g_pooled = l2norm_bwd._init_fn(gy, y, inv, 1) if ctx.normalized else gy   # d(loss)/d(pooled value)
                 nat.call("spcl_dense_rows_max_bwd", _ptr(g_pooled), _ptr(argmax), B, C, H, W, P, _ptr(gx), _stream(y))
+            elif not ctx.normalized:
+                nat.call("spcl_dense_rows_bwd", _ptr(gy), _ptr(points), B, C, H, W, ph, pw, P, _ptr(gx), _stream(y))
             else:
                 # the normalise backward is folded into the pooling backward's load phase (one launch, no g_pooled)
                 nat.call("spcl_dense_rows_bwd_fused", _ptr(gy), _ptr(y), _ptr(inv), _ptr(points), B, C, H, W, ph, pw, P,
@@ -599,14 +602,15 @@ class _DenseRows(torch.autograd.Function):
 
 
 def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: float = 1e-12,
-               pool: str = "avg") -> Tensor:
+               pool: str = "avg", normalize: bool = True) -> Tensor:
     """Unit-norm anchor rows from a dense projector output.
 
     ``x``: ``[B, C, H, W]`` (any float dtype; computed in fp32).  ``spatial_size``: the adaptive-pool target
     ``(ph, pw)`` (``None`` = no pooling); ``pool``: ``"avg"`` (``AdaptiveAvgPool2d``, the reference's default) or
     ``"max"`` (``AdaptiveMaxPool2d``, ``pool_name="adaptive_max"``).  ``points``: ``None`` for every pooled pixel (rows ordered
     ``(b, i, j)``) or an integer tensor ``[B, P]`` of flat pooled coordinates ``i * pw + j`` (rows ordered
-    ``(b, p)``).  Differentiable with respect to ``x``."""
+    ``(b, p)``).  ``normalize=False`` returns the pooled rows without the L2 normalisation.  Differentiable with
+    respect to ``x``."""
     if x.dim() != 4:
         raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
     _require_cuda(x)
@@ -628,7 +632,8 @@ def dense_rows(x: Tensor, spatial_size, points: Optional[Tensor] = None, eps: fl
         points = points.to(device=x.device, dtype=torch.int32).contiguous()
     if pool not in ("avg", "max"):
         raise ValueError(f"pool must be 'avg' or 'max', got {pool!r}")
-    y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps), pool == "max")
+    # normalize=False: the pooled rows themselves (negative eps is the kernels' "do not normalise" switch)
+    y, _ = _DenseRows.apply(x.float(), points, ph, pw, float(eps) if normalize else -1.0, pool == "max")
     return y
 
 

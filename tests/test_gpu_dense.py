@@ -177,6 +177,10 @@ def test_encoder_hook_equals_reference_pipeline():
 
 def test_dense_hook_equals_reference_pipeline():
     torch.manual_seed(1)
+    # fp32 on both sides: the head runs its last 1x1 convolution on the pooled rows (F.linear), the reference order runs
+    # it at full resolution through cuDNN, which would otherwise pick TF32 for one arm only
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     b, cin = 6, 32
     head = hooks.DenseProjectionHead(input_dim=cin, hidden_dim=64, output_dim=128, head_type="mlp", normalize=True,
                                      spatial_size=(10, 10)).cuda()
@@ -198,6 +202,9 @@ def test_dense_hook_equals_reference_pipeline():
     for p, q in zip(head.parameters(), ref_head.parameters()):
         assert (p.grad - q.grad).abs().max().item() <= 1e-4 * q.grad.abs().max().item() + 1e-9
     # forward() keeps the reference's [B, C, ph, pw] output
+    assert torch.allclose(head(fa), out[:b], atol=ROW_ATOL)
+    # the reference's order of operations (convolution at full resolution, then pool) is still available and agrees
+    head.commute_pooling = False
     assert torch.allclose(head(fa), out[:b], atol=ROW_ATOL)
 
 
