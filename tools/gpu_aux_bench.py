@@ -13,6 +13,7 @@ Algorithmic bytes = every input read once + every output written once.  ``frac``
 """
 import ctypes
 import json
+import os
 import pathlib
 import sys
 
@@ -30,8 +31,11 @@ PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROO
 def timed(fn, reps=20, flush=None):
     """Median device time between two events with the launch queue primed by a ~0.25 ms spin kernel (the host has
     enqueued fn() before the GPU reaches the start event: no Python / launch latency inside the interval)."""
-    for _ in range(3):
-        fn()
+    if os.environ.get("SPCL_AUX_ONCE"):                  # one launch per kernel: the ncu capture of tools/gpu_round.sh
+        reps = 1
+    else:
+        for _ in range(3):
+            fn()
     torch.cuda.synchronize()
     ms = []
     for _ in range(reps):

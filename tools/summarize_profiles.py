@@ -6,8 +6,12 @@ import pathlib
 import subprocess
 import sys
 
+import os
+
 ROOT = pathlib.Path(__file__).resolve().parent.parent
-OUT = ROOT / "profiles"
+# SPCL_PROFILES_OUT: write the summaries somewhere else (tools/gpu_round.sh summarises ON the GPU box into gpurun_out/,
+# so that only text travels back: the .ncu-rep files of one session exceed gpurun's 64 MiB return limit)
+OUT = pathlib.Path(os.environ.get("SPCL_PROFILES_OUT", ROOT / "profiles"))
 METRICS = [
     "gpu__time_duration.sum", "smsp__cycles_elapsed.avg.per_second", "sm__cycles_active.avg",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -76,13 +80,37 @@ def dense(tag):
     (OUT / f"{tag}_ncu_dense.txt").write_text("\n".join(out) + "\n")
 
 
+def aux(tag):
+    """every kernel of the tools/gpu_aux_bench.py capture (first launch per kernel name and grid)."""
+    rep = ROOT / "gpurun_out" / f"{tag}_prof_aux.ncu-rep"
+    if not rep.exists():
+        return
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    out = ["# ncu --set full --clock-control none -k regex:l2norm|prepare|raw_bwd|transpose  python tools/gpu_aux_bench.py",
+           "# first launch per (kernel, grid): cfg3 shapes ([32768, 128] rows / [32, 128, 32, 32]) then cfg4 shapes"]
+    seen = set()
+    for r in rows[2:]:
+        key = (r[hdr.index("Kernel Name")], r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "")
+        if key in seen:
+            continue
+        seen.add(key)
+        out.append(f"## {key[0]}  grid {key[1]}")
+        for m in METRICS:
+            if m in hdr:
+                out.append(f"{m:75s} {r[hdr.index(m)]}  {rows[1][hdr.index(m)]}")
+    (OUT / f"{tag}_ncu_aux.txt").write_text("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
-    OUT.mkdir(exist_ok=True)
+    OUT.mkdir(parents=True, exist_ok=True)
     launches(tag)
     for which in ("fwd", "bwd"):
         full(tag, which)
     dense(tag)
+    aux(tag)
     for name in ("bench.json", "bench_ref.json", "smoke.log", "pytest_gpu.log"):
         src = ROOT / "gpurun_out" / f"{tag}_{name}"
         if src.exists():
