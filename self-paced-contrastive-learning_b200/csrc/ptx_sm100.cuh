@@ -432,6 +432,17 @@ __device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, ui
       : : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Register reallocation between warpgroups (warp-specialised kernels): every warp of a warpgroup (4 consecutive warps)
+// executes the same one.  The single-thread roles give registers back, the epilogue warpgroups take them.
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

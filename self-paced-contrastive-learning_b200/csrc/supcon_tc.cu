@@ -66,6 +66,9 @@ constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp =
 // The backward's T.Z GEMM of a tile is issued in this many K-parts (1, 2 or 4), each as soon as the epilogue has
 // written its share of T: the S/T buffer's lifetime (S issue -> epilogue -> T.Z done) bounds the kernel at
 // lifetime / 3 per tile, and with one part the whole T.Z (+ its barrier hand-off) sits at the end of that chain.
+#ifndef SPCL_BWD_SETMAXNREG
+#define SPCL_BWD_SETMAXNREG 1
+#endif
 #ifndef SPCL_BWD_TZ_PARTS
 #define SPCL_BWD_TZ_PARTS 1
 #endif
@@ -1214,6 +1217,9 @@ __global__ void __launch_bounds__(256) row_finalize_kernel(const float4* __restr
 //   d_pad rows x 64 anchors.  T.Z reads it K-major (K = anchors), the S product reads the same bytes MN-major
 //   (N = anchors) -- S is an SS product and A-operand bound either way, so the fast layout goes to T.Z.
 //   The row block's own A tile still comes from Z (K-major).
+// MODE = p.mode (NONE / HARD / SOFT): one instantiation per weighting rule keeps the other rules' per-pair paths out
+// of the kernel image.
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const __grid_constant__ CUtensorMap tmap_t, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1234,6 +1240,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
   const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
   const uint32_t sbuf0 = static_cast<uint32_t>(p.d_pad);       // TMEM columns [0, d_pad) hold dZ
   const uint32_t panel_t = static_cast<uint32_t>(p.d_pad) * 128u;   // one Z^T panel: d_pad rows x 64 anchors
+#if SPCL_BWD_SETMAXNREG
+  // 384 threads x 168 registers at launch; the warpgroup of single-thread roles (warps 8-11) hands back all but 120,
+  // the two epilogue warpgroups grow to 192: the software-pipelined epilogue spilled at 168 (ptxas -v: 150-220 bytes;
+  // 0 at 192, while the single-thread roles spill below ~100)
+  if (warp >= kEpilogueWarps) reg_dealloc<120>();
+  else reg_alloc<192>();
+#endif
 
   int64_t f0, f1;
   cta_range(p, f0, f1);
@@ -1422,51 +1435,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
         const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
         const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
         const uint32_t taddr = lane_base + sbuf0 + buf * TILE;
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32b_x32(taddr, va);
-        tmem_wait_ld();
+        // The per-tile choice of the chunk body is made ONCE, outside the chunk loop, so the four chunks of the common
+        // (fast) path are one straight run of ~520 instructions.  With the choice inside the loop every chunk of the fast
+        // path sat between the unrolled bodies of the other paths (12960 instructions in the kernel): ncu's source view
+        // charged 18 % of the fast path's samples to instruction-cache misses (stall_no_inst).
+        auto run_tile = [&](auto&& chunk_body) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(taddr, va);
+          tmem_wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-          if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
-          uint32_t pk[16];
-          if (p.dbg & 1) {                                     // timing experiment: no epilogue math (results wrong)
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+            uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
+            uint32_t pk[16];
+            chunk_body(cur, ch, pk);
+            if (ch < 3) tmem_wait_ld();
+            // T (bf16) overwrites S columns [16 ch, 16 ch + 16), all of which were loaded before
+            tmem_st_32x32b_x16(taddr + ch * 16, pk);
+            constexpr int kChPerPart = 4 / SPCL_BWD_TZ_PARTS;
+            if ((ch + 1) % kChPerPart == 0) {                 // this K-part of T is complete: its T.Z may be issued
+              tmem_wait_st();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar->t_full[buf][(ch + 1) / kChPerPart - 1]);
+            }
+          }
+        };
+        if (p.dbg & 1) {                                       // timing experiment: no epilogue math (results wrong)
+          run_tile([&](const uint32_t(&cur)[32], int, uint32_t(&pk)[16]) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) pk[e] = cur[2 * e] ^ cur[2 * e + 1];
-          } else if (!slow) {
+          });
+        } else if (!slow) {
+          run_tile([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
 #if SPCL_BWD_SWP
             bwd_chunk_fast_swp(cur, smem_u32(u_s + ch * 32), ek, uiui, pk);
 #else
             bwd_chunk_fast(cur, u_s + ch * 32, ek, uiui, pk);
 #endif
-          } else if (allpos && row_ok) {
-            if (p.mode == SPCL_MODE_SOFT)
-              bwd_chunk_allpos<SPCL_MODE_SOFT>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
-            else if (p.mode == SPCL_MODE_HARD)
-              bwd_chunk_allpos<SPCL_MODE_HARD>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
-            else
-              bwd_chunk_allpos<SPCL_MODE_NONE>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
-          } else if (p.mode == SPCL_MODE_SOFT) {
-            bwd_chunk_slow<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
-                                           u_i, pk);
-          } else if (p.mode == SPCL_MODE_HARD) {
-            bwd_chunk_slow<SPCL_MODE_HARD>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
-                                           u_i, pk);
-          } else {
-            bwd_chunk_slow<SPCL_MODE_NONE>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i,
-                                           u_i, pk);
-          }
-          if (ch < 3) tmem_wait_ld();
-          // T (bf16) overwrites S columns [16 ch, 16 ch + 16), all of which were loaded before
-          tmem_st_32x32b_x16(taddr + ch * 16, pk);
-          constexpr int kChPerPart = 4 / SPCL_BWD_TZ_PARTS;
-          if ((ch + 1) % kChPerPart == 0) {                   // this K-part of T is complete: its T.Z may be issued
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar->t_full[buf][(ch + 1) / kChPerPart - 1]);
-          }
+          });
+        } else if (allpos && row_ok) {
+          run_tile([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
+            bwd_chunk_allpos<MODE>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
+          });
+        } else {
+          run_tile([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
+            bwd_chunk_slow<MODE>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i, u_i, pk);
+          });
         }
         TRACE(2 + warp, c.it, 1);
       }
@@ -2218,7 +2234,9 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
     }
   }
   const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot, 128, true) + 1024;
-  rc = tc::set_smem(tc::bwd_kernel, smem);
+  auto kern = mode == SPCL_MODE_SOFT ? tc::bwd_kernel<SPCL_MODE_SOFT>
+              : mode == SPCL_MODE_HARD ? tc::bwd_kernel<SPCL_MODE_HARD> : tc::bwd_kernel<SPCL_MODE_NONE>;
+  rc = tc::set_smem(kern, smem);
   if (rc != SPCL_OK) return rc;
   CUtensorMap tmap_t;
   rc = tc::make_zt_tensor_map(&tmap_t, zt, n_pad, d_pad);
@@ -2227,7 +2245,7 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
       static_cast<const uint16_t*>(zb), static_cast<uint16_t*>(zt), n_pad, d_pad);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16/transpose");
   SPCL_CUDA_TRY(cudaMemsetAsync(dz, 0, static_cast<size_t>(row_end - row_begin) * lddz * sizeof(float), s));
-  tc::bwd_kernel<<<tc::grid_for(p), tc::NTHREADS, smem, s>>>(tmap, tmap_t, p);
+  kern<<<tc::grid_for(p), tc::NTHREADS, smem, s>>>(tmap, tmap_t, p);
   SPCL_LAUNCH_CHECK("spcl_supcon_bwd_bf16");
   return SPCL_OK;
 }
