@@ -191,6 +191,7 @@ def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Op
         if runner is None:
             if len(graph_cache) >= 8:             # gamma changes once per epoch: keep the cache small
                 graph_cache.pop(next(iter(graph_cache)))
+                _note_graph_eviction()
             runner = graph_cache[key] = ops.GraphRunner(n, z1.shape[1], dev, temperature, gamma, mode, correct_grad,
                                                         use_tc)
         scalars, row_stats = ops.supcon_fwd_graphed(z1, z2, labels, runner)
@@ -198,6 +199,20 @@ def supcon_loss(proj_feat1: Tensor, proj_feat2: Tensor, *, target=None, mask: Op
         scalars, row_stats = ops.supcon_fwd_eager(z1, z2, labels, tri, float(temperature), float(gamma), int(mode),
                                                   bool(correct_grad), use_tc)
     return scalars[0], scalars, dict(labels=labels, tri=tri, row_stats=row_stats, use_tc=use_tc)
+
+
+_GRAPH_EVICTIONS = [0]
+
+
+def _note_graph_eviction():
+    """gamma (and every other hyper-parameter) is baked into a captured graph: a caller that changes gamma on every
+    step instead of once per epoch (infonce.py:134-136) recaptures a graph per call, which is slower than eager."""
+    _GRAPH_EVICTIONS[0] += 1
+    if _GRAPH_EVICTIONS[0] == 32:
+        import warnings
+        warnings.warn("spcl_b200: cuda_graph=True keeps recapturing graphs (32 evictions): the captured graph is keyed by "
+                      "(batch shape, temperature, gamma, mode); change gamma once per epoch or use cuda_graph=False",
+                      RuntimeWarning, stacklevel=3)
 
 
 class _FusedSupConBase(nn.Module):
