@@ -732,6 +732,225 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variants of the fused projector tail (round 2): x is read from HBM ONCE and kept in registers
+// (the kernels above read it once for the norms / the dot product and again for the output: 46 % / 21 % of the copy
+// bandwidth at cfg4 sizes).  A CTA owns TA anchors; thread (a, g) holds channels g, g + 4, ... of anchor a, so loads and
+// stores along the pixels stay coalesced; the row-major side (zb / dz) goes through one padded shared-memory tile.
+// KC = channels per thread (d <= 4 * KC).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRawG = 4;
+
+template <int KC>
+__global__ void __launch_bounds__(512) prepare_raw_reg_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                              int64_t n, int d, int64_t inner, float eps,
+                                                              const int32_t* __restrict__ labels,
+                                                              __nv_bfloat16* __restrict__ zb, int d_pad,
+                                                              float* __restrict__ inv_norm,
+                                                              int32_t* __restrict__ labels_full, int4* __restrict__ sig,
+                                                              float* __restrict__ partials) {
+  extern __shared__ __align__(16) uint8_t raw_smem[];
+  const int ldt = d_pad + 2;                                         // bf16 elements per tile row (65 / 129 words: no conflicts)
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(raw_smem);  // [SPCL_TILE][ldt]
+  float* ssp = reinterpret_cast<float*>(raw_smem + static_cast<size_t>(SPCL_TILE) * ldt * 2);   // [kRawG][SPCL_TILE]
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * SPCL_TILE;
+  const int a = threadIdx.x & (SPCL_TILE - 1), g = threadIdx.x >> 7;
+  bool ok;
+  const float* base = raw_base(x1, x2, n, d, inner, row0 + a, ok);
+  float xv[KC];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawG * k;
+    xv[k] = (ok && c < d) ? base[static_cast<int64_t>(c) * inner] : 0.f;
+    ss = fmaf(xv[k], xv[k], ss);
+  }
+  ssp[g * SPCL_TILE + a] = ss;
+  __syncthreads();
+  ss = ssp[a] + ssp[SPCL_TILE + a] + ssp[2 * SPCL_TILE + a] + ssp[3 * SPCL_TILE + a];
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  if (g == 0 && ok) inv_norm[row0 + a] = inv;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawG * k;
+    if (c < d_pad) tile[a * ldt + c] = __float2bfloat16_rn(xv[k] * inv);      // xv == 0 beyond d and beyond the last anchor
+  }
+  __syncthreads();
+  const int groups = d_pad >> 3;                                       // 16-byte groups per row
+  for (int idx = threadIdx.x; idx < SPCL_TILE * groups; idx += blockDim.x) {
+    const int r = idx / groups, cg = (idx % groups) << 3;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile + r * ldt + cg);   // 4-byte aligned (ldt, cg even)
+    uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+    *reinterpret_cast<uint4*>(zb + (row0 + r) * d_pad + cg) = v;
+  }
+  // labels, block signature, partial sums: as prepare_kernel
+  const int64_t n_total = 2 * n;
+  if (threadIdx.x < SPCL_TILE) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = row0 + threadIdx.x;
+    int mn = INT_MAX, mx = INT_MIN;
+    unsigned lo = 0u, hi = 0u;
+    int v = 0;
+    if (i < n_total) {
+      const int64_t h = i < n ? i : i - n;
+      v = labels != nullptr ? labels[h] : static_cast<int32_t>(h);
+      mn = mx = v;
+      const unsigned hsh = (static_cast<unsigned>(v) * 0x9E3779B1u) >> 26;
+      if (hsh < 32) lo = 1u << hsh; else hi = 1u << (hsh - 32);
+    }
+    labels_full[i] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+      hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    __shared__ int s_mn[4], s_mx[4];
+    __shared__ unsigned s_lo[4], s_hi[4];
+    if (lane == 0) {
+      s_mn[threadIdx.x >> 5] = mn;
+      s_mx[threadIdx.x >> 5] = mx;
+      s_lo[threadIdx.x >> 5] = lo;
+      s_hi[threadIdx.x >> 5] = hi;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        mn = min(mn, s_mn[k]);
+        mx = max(mx, s_mx[k]);
+        lo |= s_lo[k];
+        hi |= s_hi[k];
+      }
+      sig[blockIdx.x] = make_int4(mn, mx, static_cast<int>(lo), static_cast<int>(hi));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x >= 128 && threadIdx.x < 131) partials[threadIdx.x - 128] = 0.f;
+}
+
+constexpr int kRawTA = 64;                                           // anchors per CTA of the backward
+
+template <int KC>
+__global__ void __launch_bounds__(256) raw_bwd_reg_kernel(const float* __restrict__ dz, int64_t lddz,
+                                                          const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          const float* __restrict__ inv_norm, float* __restrict__ gx1,
+                                                          float* __restrict__ gx2, int64_t n, int d, int64_t inner) {
+  extern __shared__ __align__(16) uint8_t raw_smem[];
+  const int ldt = d + 1;
+  float* tile = reinterpret_cast<float*>(raw_smem);                  // dz rows [kRawTA][ldt]
+  float* dotp = tile + kRawTA * ldt;                                 // [kRawG][kRawTA]
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRawTA;
+  const int a = threadIdx.x & (kRawTA - 1), g = threadIdx.x >> 6;
+  {                                                                  // dz rows are contiguous: a warp per row, coalesced along c
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < kRawTA; r += 8) {
+      const int64_t gr = row0 + r;
+      const bool rok = gr < 2 * n;
+      const float* src = dz + gr * lddz;
+      for (int c = lane; c < d; c += 32) tile[r * ldt + c] = rok ? __ldg(src + c) : 0.f;
+    }
+  }
+  bool ok;
+  const float* base = raw_base(x1, x2, n, d, inner, row0 + a, ok);
+  float* gbase = ok ? ((row0 + a) < n ? gx1 : gx2) + (base - ((row0 + a) < n ? x1 : x2)) : nullptr;
+  const float inv = ok ? inv_norm[row0 + a] : 0.f;
+  float xv[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawG * k;
+    xv[k] = (ok && c < d) ? base[static_cast<int64_t>(c) * inner] * inv : 0.f;      // y = x * inv
+  }
+  __syncthreads();
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawG * k;
+    if (c < d) dot = fmaf(xv[k], tile[a * ldt + c], dot);
+  }
+  dotp[g * kRawTA + a] = dot;
+  __syncthreads();
+  dot = dotp[a] + dotp[kRawTA + a] + dotp[2 * kRawTA + a] + dotp[3 * kRawTA + a];
+  if (!ok) return;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawG * k;
+    if (c < d) gbase[static_cast<int64_t>(c) * inner] = inv * (tile[a * ldt + c] - xv[k] * dot);
+  }
+}
+
+// The same with 16-byte accesses along the pixels (inner % 4 == 0): thread (g, l) owns 4 consecutive anchors (one
+// float4 per channel) and channels g, g + 16, ...; 16 channel groups x 16 lanes = 256 threads, 64 anchors per CTA.
+constexpr int kRawVG = 16;
+
+template <int KC>
+__global__ void __launch_bounds__(256) raw_bwd_vec_kernel(const float* __restrict__ dz, int64_t lddz,
+                                                          const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          const float* __restrict__ inv_norm, float* __restrict__ gx1,
+                                                          float* __restrict__ gx2, int64_t n, int d, int64_t inner) {
+  extern __shared__ __align__(16) uint8_t raw_smem[];
+  const int ldt = d + 1;
+  float* tile = reinterpret_cast<float*>(raw_smem);                  // dz rows [kRawTA][ldt]
+  float* dotp = tile + kRawTA * ldt;                                 // [kRawVG][kRawTA]
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRawTA;
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < kRawTA; r += 8) {
+      const int64_t gr = row0 + r;
+      const bool rok = gr < 2 * n;
+      const float* src = dz + gr * lddz;
+      for (int c = lane; c < d; c += 32) tile[r * ldt + c] = rok ? __ldg(src + c) : 0.f;
+    }
+  }
+  const int l = threadIdx.x & 15, g = threadIdx.x >> 4;
+  const int a0 = 4 * l;
+  bool ok;
+  const float* base = raw_base(x1, x2, n, d, inner, row0 + a0, ok);   // n % 4 == 0: the 4 anchors are valid together
+  float* gbase = ok ? ((row0 + a0) < n ? gx1 : gx2) + (base - ((row0 + a0) < n ? x1 : x2)) : nullptr;
+  const float4 inv = ok ? *reinterpret_cast<const float4*>(inv_norm + row0 + a0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 yv[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawVG * k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && c < d) v = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(c) * inner);
+    yv[k] = make_float4(v.x * inv.x, v.y * inv.y, v.z * inv.z, v.w * inv.w);             // y = x * inv
+  }
+  __syncthreads();
+  float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawVG * k;
+    if (c < d) {
+      dot.x = fmaf(yv[k].x, tile[(a0 + 0) * ldt + c], dot.x);
+      dot.y = fmaf(yv[k].y, tile[(a0 + 1) * ldt + c], dot.y);
+      dot.z = fmaf(yv[k].z, tile[(a0 + 2) * ldt + c], dot.z);
+      dot.w = fmaf(yv[k].w, tile[(a0 + 3) * ldt + c], dot.w);
+    }
+  }
+  *reinterpret_cast<float4*>(dotp + g * kRawTA + a0) = dot;
+  __syncthreads();
+  dot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < kRawVG; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(dotp + q * kRawTA + a0);
+    dot.x += t.x; dot.y += t.y; dot.z += t.z; dot.w += t.w;
+  }
+  if (!ok) return;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + kRawVG * k;
+    if (c < d) {
+      float4 o;
+      o.x = inv.x * (tile[(a0 + 0) * ldt + c] - yv[k].x * dot.x);
+      o.y = inv.y * (tile[(a0 + 1) * ldt + c] - yv[k].y * dot.y);
+      o.z = inv.z * (tile[(a0 + 2) * ldt + c] - yv[k].z * dot.z);
+      o.w = inv.w * (tile[(a0 + 3) * ldt + c] - yv[k].w * dot.w);
+      *reinterpret_cast<float4*>(gbase + static_cast<int64_t>(c) * inner) = o;
+    }
+  }
+}
+
 }  // namespace aux
 }  // namespace spcl
 
@@ -849,9 +1068,25 @@ extern "C" int spcl_supcon_prepare_raw_bf16(const float* x1, const float* x2, in
   if (d_pad < d || d_pad % 64 != 0 || d_pad > SPCL_MAX_D) return SPCL_ERR_UNSUPPORTED;
   if (n_pad < 2 * n || n_pad % SPCL_TILE != 0 || n_pad - 2 * n >= SPCL_TILE) return SPCL_ERR_INVALID_ARG;
   if (!aux::aligned16(zb) || !aux::aligned16(sig)) return SPCL_ERR_INVALID_ARG;
-  aux::prepare_raw_kernel<<<static_cast<unsigned>(n_pad / SPCL_TILE), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x1, x2, n, static_cast<int>(d), inner, eps, labels, static_cast<__nv_bfloat16*>(zb), static_cast<int>(d_pad),
-      inv_norm, labels_full, reinterpret_cast<int4*>(sig), partials);
+  static const bool legacy = getenv("SPCL_RAW_LEGACY") != nullptr;        // A/B switch: the two-pass kernels
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>(n_pad / SPCL_TILE);
+  if (legacy) {
+    aux::prepare_raw_kernel<<<grid, 256, 0, s>>>(x1, x2, n, static_cast<int>(d), inner, eps, labels,
+                                                 static_cast<__nv_bfloat16*>(zb), static_cast<int>(d_pad), inv_norm,
+                                                 labels_full, reinterpret_cast<int4*>(sig), partials);
+  } else {
+    const size_t smem = static_cast<size_t>(SPCL_TILE) * (d_pad + 2) * 2 + aux::kRawG * SPCL_TILE * sizeof(float);
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024)
+        SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<grid, 512, smem, s>>>(x1, x2, n, static_cast<int>(d), inner, eps, labels, static_cast<__nv_bfloat16*>(zb),
+                                   static_cast<int>(d_pad), inv_norm, labels_full, reinterpret_cast<int4*>(sig), partials);
+      return SPCL_OK;
+    };
+    const int rc = d_pad <= 128 ? launch(aux::prepare_raw_reg_kernel<32>) : launch(aux::prepare_raw_reg_kernel<64>);
+    if (rc != SPCL_OK) return rc;
+  }
   SPCL_LAUNCH_CHECK("spcl_supcon_prepare_raw_bf16");
   return SPCL_OK;
 }
@@ -863,9 +1098,38 @@ extern "C" int spcl_supcon_raw_bwd(const float* dz, int64_t lddz, const float* x
       outer <= 0 || d <= 0 || inner <= 0 || lddz < d)
     return SPCL_ERR_INVALID_ARG;
   const int64_t n = outer * inner;
-  aux::raw_bwd_kernel<<<static_cast<unsigned>(ceil_div(2 * n, static_cast<int64_t>(SPCL_TILE))), 256, 0,
-                        static_cast<cudaStream_t>(stream)>>>(dz, lddz, x1, x2, inv_norm, gx1, gx2, n,
-                                                             static_cast<int>(d), inner);
+  static const bool legacy = getenv("SPCL_RAW_LEGACY") != nullptr;        // A/B switch: the two-pass kernel
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (legacy || d > SPCL_MAX_D) {
+    aux::raw_bwd_kernel<<<static_cast<unsigned>(ceil_div(2 * n, static_cast<int64_t>(SPCL_TILE))), 256, 0, s>>>(
+        dz, lddz, x1, x2, inv_norm, gx1, gx2, n, static_cast<int>(d), inner);
+  } else {
+    const size_t smem = (static_cast<size_t>(aux::kRawTA) * (d + 1) + aux::kRawG * aux::kRawTA) * sizeof(float);
+    const unsigned grid = static_cast<unsigned>(ceil_div(2 * n, static_cast<int64_t>(aux::kRawTA)));
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024)
+        SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<grid, 256, smem, s>>>(dz, lddz, x1, x2, inv_norm, gx1, gx2, n, static_cast<int>(d), inner);
+      return SPCL_OK;
+    };
+    const bool vec = inner % 4 == 0 && aux::aligned16(x1) && aux::aligned16(x2) && aux::aligned16(gx1) &&
+                     aux::aligned16(gx2) && aux::aligned16(inv_norm);
+    int rc;
+    if (vec) {
+      // the dot-product scratch is [16][64] floats here (4 KB) instead of [4][64]
+      const size_t smem_v = (static_cast<size_t>(aux::kRawTA) * (d + 1) + aux::kRawVG * aux::kRawTA) * sizeof(float);
+      auto launch_v = [&](auto kern) -> int {
+        if (smem_v > 48 * 1024)
+          SPCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_v)));
+        kern<<<grid, 256, smem_v, s>>>(dz, lddz, x1, x2, inv_norm, gx1, gx2, n, static_cast<int>(d), inner);
+        return SPCL_OK;
+      };
+      rc = d <= 128 ? launch_v(aux::raw_bwd_vec_kernel<8>) : launch_v(aux::raw_bwd_vec_kernel<16>);
+    } else {
+      rc = d <= 128 ? launch(aux::raw_bwd_reg_kernel<32>) : launch(aux::raw_bwd_reg_kernel<64>);
+    }
+    if (rc != SPCL_OK) return rc;
+  }
   SPCL_LAUNCH_CHECK("spcl_supcon_raw_bwd");
   return SPCL_OK;
 }
