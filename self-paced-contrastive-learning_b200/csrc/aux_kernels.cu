@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) l2norm_strided_bwd(const T* __restrict__ 
 //          the copy bandwidth.)
 // ------------------------------------------------------------------------------------------------
 template <typename T, int V, int NV, int R>
-__global__ void __launch_bounds__(256) l2norm_rows_fwd_reg(const T* __restrict__ x, T* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) l2norm_rows_fwd_reg(const T* __restrict__ x, T* __restrict__ y,
                                                            float* __restrict__ inv_norm, int64_t rows, int d,
                                                            float eps) {
   const int lane = threadIdx.x & 31;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) l2norm_rows_fwd_reg(const T* __restrict__
 }
 
 template <typename T, int V, int NV, int R>
-__global__ void __launch_bounds__(256) l2norm_rows_bwd_reg(const T* __restrict__ gy, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) l2norm_rows_bwd_reg(const T* __restrict__ gy, const T* __restrict__ y,
                                                            const float* __restrict__ inv_norm, T* __restrict__ gx,
                                                            int64_t rows, int d) {
   const int lane = threadIdx.x & 31;
@@ -286,7 +286,8 @@ constexpr int kStrG = 16, kStrL = 16;     // channel groups x lanes along `inner
 
 // BWD = false: y = x * inv, inv_norm out.  BWD = true: gx = inv * (gy - y * sum_c(y gy)) with a = gy, b = y.
 template <typename T, int V, int KC, bool BWD>
-__global__ void __launch_bounds__(256) l2norm_strided_reg(const T* __restrict__ a_in, const T* __restrict__ b_in,
+// (min-blocks: left alone ptxas spent 102-136 registers on unrolled 64-bit addresses: 2 CTAs per SM, 23 % of the warp slots)
+__global__ void __launch_bounds__(256, (KC <= 8 ? 3 : 2)) l2norm_strided_reg(const T* __restrict__ a_in, const T* __restrict__ b_in,
                                                           T* __restrict__ out, float* __restrict__ inv_norm,
                                                           int d, int64_t inner, int64_t tiles_per_image, float eps) {
   __shared__ float part[kStrG][kStrL * V + 1];

@@ -66,6 +66,9 @@ constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp =
 // The backward's T.Z GEMM of a tile is issued in this many K-parts (1, 2 or 4), each as soon as the epilogue has
 // written its share of T: the S/T buffer's lifetime (S issue -> epilogue -> T.Z done) bounds the kernel at
 // lifetime / 3 per tile, and with one part the whole T.Z (+ its barrier hand-off) sits at the end of that chain.
+#ifndef SPCL_FWD_SETMAXNREG
+#define SPCL_FWD_SETMAXNREG 0
+#endif
 #ifndef SPCL_BWD_SETMAXNREG
 #define SPCL_BWD_SETMAXNREG 1
 #endif
@@ -788,6 +791,12 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
   const uint32_t tmem_base = bar->tmem_base;
   const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);   // provably warp-uniform copy for the MMA issuer
 
+#if SPCL_FWD_SETMAXNREG
+  if (NWG == 2) {                                   // see bwd_kernel: 384 threads x 168 registers at launch
+    if (warp >= kEpilogueWarps) reg_dealloc<120>();
+    else reg_alloc<192>();
+  }
+#endif
   const CtaRange range = cta_range_of(p, BN);
   constexpr int kSymShift = SYM ? (kSub == 2 ? 1 : 0) : -1;
   const uint32_t a_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES;
