@@ -284,9 +284,35 @@ struct Ring {
 // One lane polls the mbarrier, the warp joins at __syncwarp: a probe by all 32 lanes is serialised in the
 // synchronisation unit and cost 150-350 cycles per wait in the epilogue warps (timeline: ~600-800 idle cycles
 // between two tiles of a warpgroup).
+// (round 2) SPCL_TRYWAIT = 1: every lane blocks in mbarrier.try_wait instead -- the hardware parks the warp until the
+// phase completes (or its time limit passes) and wakes it without a software poll round trip: the consumer saw a
+// completed barrier 200-450 cycles later with the one-lane test_wait spin (timeline r02w: the four warps of a warpgroup
+// noticed the same S tile up to 450 cycles apart).  Same-session A/B (r02z): backward 481 -> 459 us with the epilogue's
+// waits alone.
+#ifndef SPCL_TRYWAIT
+#define SPCL_TRYWAIT 1
+#endif
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPCL_MBAR_TIMEOUT_NS) {
+        printf("spcl: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+#if SPCL_TRYWAIT
+  mbar_wait_all(bar, parity);
+#else
   if (lane == 0) mbar_wait(bar, parity);
   __syncwarp();
+#endif
 }
 
 // Calls f(t) for every column tile of [tb, te) the sp pass has to visit, in order, warp-uniformly: only
@@ -843,12 +869,9 @@ __global__ void __launch_bounds__(32 * (4 * NWG + 4), 1) stats_kernel(const __gr
     Ring rs(p.nslot), rb(kBufs);
     for (TileCursor c(range, p.CT, p.RB, kSymShift); c.valid(); c.next(), rs.next(), rb.next()) {
       if ((c.it & 1) != mw) continue;
-      if (lane == 0) {
-        if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
-        mbar_wait(&bar->full[rs.idx], rs.ph);
-        mbar_wait(&bar->s_empty[rb.idx], rb.ph ^ 1);
-      }
-      __syncwarp();
+      if (c.first()) mbar_wait_warp(&bar->a_full, c.seg & 1, lane);
+      mbar_wait_warp(&bar->full[rs.idx], rs.ph, lane);
+      mbar_wait_warp(&bar->s_empty[rb.idx], rb.ph ^ 1, lane);
       if (c.it != 0) named_bar_sync(1 + mw, 64);              // tile it - 1 has been issued
       TRACE(1, c.it, 0);
       tc_fence_after();
@@ -1071,11 +1094,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
         if ((it & 1) == mw) {
           const int slot = it % p.nslot, buf = it % p.nbuf;
           const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
-          if (lane == 0) {
-            mbar_wait(&bar->full[slot], ph);
-            mbar_wait(&bar->s_empty[buf], bph ^ 1);
-          }
-          __syncwarp();
+          mbar_wait_warp(&bar->full[slot], ph, lane);
+          mbar_wait_warp(&bar->s_empty[buf], bph ^ 1, lane);
           tc_fence_after();
           if (elect_one()) {
             issue_s_mma<TILE>(tmem_u + buf * TILE, a_base, smem_u32(sm.slot(slot)), 0, nk);
@@ -1116,11 +1136,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const int64_t dj = gi - j0;
           const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
           const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
-          if (lane == 0) {
-            mbar_wait(&bar->full[slot], ph);
-            mbar_wait(&bar->s_full[buf], bph);
-          }
-          __syncwarp();
+          mbar_wait_warp(&bar->full[slot], ph, lane);
+          mbar_wait_warp(&bar->s_full[buf], bph, lane);
           tc_fence_after();
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
@@ -1300,12 +1317,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
     const uint32_t nb = static_cast<uint32_t>(p.nbuf);
     Ring ss(p.nslot), sb(p.nbuf);
     for (TileCursor c(f0, f1, p.CT); c.valid(); c.next(), ss.next(), sb.next()) {
-      if (lane == 0) {
-        if (c.first()) mbar_wait(&bar->a_full, c.seg & 1);
-        mbar_wait(&bar->full[ss.idx], ss.ph);
-        if (safe) mbar_wait(&bar->s_empty[sb.idx], sb.ph ^ 1);
-      }
-      __syncwarp();
+      if (c.first()) mbar_wait_warp(&bar->a_full, c.seg & 1, lane);
+      mbar_wait_warp(&bar->full[ss.idx], ss.ph, lane);
+      if (safe) mbar_wait_warp(&bar->s_empty[sb.idx], sb.ph ^ 1, lane);
       if (c.it >= nb) named_bar_sync(1, 64);                  // T.Z(it - nbuf) has been issued
       TRACE(1, c.it, 0);
       tc_fence_after();
@@ -1342,11 +1356,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
       constexpr int kParts = SPCL_BWD_TZ_PARTS, kPerPart = (TILE / 16) / kParts;
 #pragma unroll
       for (int part = 0; part < kParts; ++part) {
-        if (lane == 0) {
-          mbar_wait(&bar->t_full[tb.idx][part], tb.ph);       // T columns of this K-part written
-          if (first && part == 0) mbar_wait(&bar->dz_empty, (c.seg & 1) ^ 1);
-        }
-        __syncwarp();
+        mbar_wait_warp(&bar->t_full[tb.idx][part], tb.ph, lane);       // T columns of this K-part written
+        if (first && part == 0) mbar_wait_warp(&bar->dz_empty, (c.seg & 1) ^ 1, lane);
         if (part == 0) {
           if (c.it + nb - 1 < c.n) named_bar_sync(2, 64);     // S(it + nbuf - 1) has been issued
           TRACE(1, c.it, 2);
@@ -1429,11 +1440,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
         }
         const bool slow = ((mask >> (c.t & 31)) & 1u) != 0u;
         const bool allpos = ((apmask >> (c.t & 31)) & 1u) != 0u;
-        if (lane == 0) {
-          mbar_wait(&bar->full[slot], ph);
-          mbar_wait(&bar->s_full[buf], bph);
-        }
-        __syncwarp();
+        mbar_wait_warp(&bar->s_full[buf], bph, lane);
+        mbar_wait_warp(&bar->full[slot], ph, lane);           // (implied by s_full; completes at once)
         TRACE(2 + warp, c.it, 0);
         tc_fence_after();
         const int32_t* lab_s = sm.slot_labels(slot);
