@@ -66,6 +66,11 @@ constexpr int kEpilogueWarps = 8, kProducerWarp = 8, kMmaWarp0 = 9, kAllocWarp =
 // The backward's T.Z GEMM of a tile is issued in this many K-parts (1, 2 or 4), each as soon as the epilogue has
 // written its share of T: the S/T buffer's lifetime (S issue -> epilogue -> T.Z done) bounds the kernel at
 // lifetime / 3 per tile, and with one part the whole T.Z (+ its barrier hand-off) sits at the end of that chain.
+// The backward's own row block (the A operand of S = Z_I Z_J^T) staged from Z^T and read MN-major (1) or from Z and
+// read K-major (0).
+#ifndef SPCL_BWD_A_MN
+#define SPCL_BWD_A_MN 0
+#endif
 #ifndef SPCL_FWD_SETMAXNREG
 #define SPCL_FWD_SETMAXNREG 0
 #endif
@@ -1287,7 +1292,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
           const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
           mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
           mbar_arrive_expect_tx(&bar->a_full, static_cast<uint32_t>(p.dc) * CHUNK_BYTES);
+#if SPCL_BWD_A_MN
+          for (int h = 0; h < 2; ++h) tma_load_2d(sm.a_tile + h * panel_t, &tmap_t, &bar->a_full, gi0 + h * 64, 0);
+#else
           for (int k = 0; k < p.dc; ++k) tma_load_2d(sm.a_tile + k * CHUNK_BYTES, &tmap, &bar->a_full, k * 64, gi0);
+#endif
         }
         const int slot = rs.idx;
         mbar_wait(&bar->empty[slot], rs.ph ^ 1);
@@ -1326,14 +1335,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
       if (elect_one()) {
         // S = Z_I (K-major A) x Z^T slot read MN-major: the 64-anchor MN atoms are the two panels (LBO = panel
         // bytes), 8-row K (= d) groups are 1024 B apart (SBO); each K = 16 step advances 16 rows.
-        constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, false, true);
+        constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, SPCL_BWD_A_MN != 0, true);
         const uint32_t d_tmem = tmem_u + sbuf0 + sb.idx * TILE;
         const uint32_t b_base = smem_u32(sm.slot(ss.idx));
         const int nk_s = (p.dbg & 2048) ? 1 : nk;             // timing experiment: one K step only (results wrong)
         for (int kk = 0; kk < nk_s; ++kk) {
+#if SPCL_BWD_A_MN
+          const uint64_t ad = make_smem_desc_sw128(a_base + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024);
+#else
           const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
-          mma_ss(d_tmem, make_smem_desc_sw128(a_base + pa, 16, 1024),
-                 make_smem_desc_sw128(b_base + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024), idesc_s,
+          const uint64_t ad = make_smem_desc_sw128(a_base + pa, 16, 1024);
+#endif
+          mma_ss(d_tmem, ad, make_smem_desc_sw128(b_base + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024), idesc_s,
                  kk != 0 ? 1u : 0u);
         }
         tc_commit(&bar->s_full[sb.idx]);
@@ -1518,6 +1531,331 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_kernel(const __grid_constant_
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const int col = c0 + e;
+              if (col < p.d) atomicAdd(out + col, __uint_as_float(v[e]) * coef);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->dz_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kAllocWarp) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// backward on 128 x 256 S tiles (d_pad <= 128, even number of column tiles)
+// =================================================================================================
+// tools/mma_bench.cu: an SS tcgen05.mma of M = 128 takes 98-137 cycles per K = 16 step for ANY N <= 256 and either
+// layout of A or B (the shared-memory A operand bounds it), while N = 256 is at the pipe's floor (128 cycles): two
+// column tiles per S instruction halve the S product's time (8 x 129 cycles for 2 tiles instead of 2 x 8 x 98-137).
+// TMEM (512 columns):  dZ [0, 128)  |  S pair [128, 384): tiles 2k, 2k + 1  |  T [384, 512): 2 x 64 columns of bf16.
+//   * one S buffer: S(k + 1) is issued as soon as the eight epilogue warps have LOADED S(k) (s_free), not when T.Z(k)
+//     has run -- T is written to its own columns instead of over S;
+//   * both epilogue warpgroups work on the SAME tile (warpgroup w: S columns [64 w, 64 w + 64) of it), first on
+//     tile 2k, then on 2k + 1: T(2k) is complete after half of the pair's epilogue and T.Z(2k) runs under the rest;
+//   * the two issuer warps need no hand-off: nothing one of them writes is read by the other's MMAs.
+//   Pipe order in steady state:  S(k) | T.Z(2k) | S(k + 1) | T.Z(2k + 1) | T.Z(2k + 2) | S(k + 2) ...
+// Column tiles keep their own 32 KB slots (ring of p.nslot); the B operand of an S pair is the two slots' four Z^T
+// panels read MN-major with one stride, so the pair must sit in adjacent slots: when the ring wraps between them
+// (odd p.nslot: one pair in nslot) the S pair is issued as two N = 128 products instead.
+struct BarriersW {
+  uint64_t full[kMaxSlots];      // column tile landed in the slot (Z^T panels + labels + column statistics)
+  uint64_t empty[kMaxSlots];     // T.Z of the tile in the slot has completed
+  uint64_t s_full;               // S pair complete
+  uint64_t s_free;               // all eight epilogue warps hold their share of the S pair in registers
+  uint64_t t_full[2];            // T of tile x of the pair written by all eight warps
+  uint64_t t_free[2];            // T.Z of tile x has completed: its T columns may be overwritten
+  uint64_t a_full, a_empty, dz_full, dz_empty;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(BarriersW) <= sizeof(Barriers), "BarriersW lives in the space carve() reserves for Barriers");
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                               const __grid_constant__ CUtensorMap tmap_t, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sm = carve(smem_raw, p, TILE, true);
+  BarriersW* bar = reinterpret_cast<BarriersW*>(sm.bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kMmaWarp0 && lane == 0) {
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&bar->full[i], 1);
+      mbar_init(&bar->empty[i], 1);
+    }
+    mbar_init(&bar->s_full, 1);
+    mbar_init(&bar->s_free, 8);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&bar->t_full[x], 8);
+      mbar_init(&bar->t_free[x], 1);
+    }
+    mbar_init(&bar->a_full, 1);
+    mbar_init(&bar->a_empty, 1);
+    mbar_init(&bar->dz_full, 1);
+    mbar_init(&bar->dz_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == kAllocWarp) tmem_alloc<kTmemCols>(&bar->tmem_base);
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tensormap(&tmap);
+    prefetch_tensormap(&tmap_t);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_base;
+  const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
+  constexpr uint32_t kSCol = 128, kTCol = 384;                     // TMEM columns of the S pair and of T
+  const uint32_t panel_t = static_cast<uint32_t>(p.d_pad) * 128u;   // one Z^T panel: d_pad rows x 64 anchors
+#if SPCL_BWD_SETMAXNREG
+  if (warp >= kEpilogueWarps) reg_dealloc<120>();
+  else reg_alloc<192>();
+#endif
+
+  int64_t f0, f1;
+  cta_range(p, f0, f1);                                  // p.CT = PAIRS of column tiles per row block
+  const int64_t rb0 = p.row_begin / TILE, I0 = f0 / p.CT;
+  const uint32_t tile_tx = static_cast<uint32_t>(p.dc) * CHUNK_BYTES + META_BYTES;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      Ring rs(p.nslot);
+      for (TileCursor c(f0, f1, p.CT); c.valid(); c.next()) {
+        if (c.first()) {
+          const int32_t gi0 = static_cast<int32_t>(p.row_begin + (I0 + c.seg) * TILE);
+          mbar_wait(&bar->a_empty, (c.seg & 1) ^ 1);
+          mbar_arrive_expect_tx(&bar->a_full, static_cast<uint32_t>(p.dc) * CHUNK_BYTES);
+          for (int k = 0; k < p.dc; ++k) tma_load_2d(sm.a_tile + k * CHUNK_BYTES, &tmap, &bar->a_full, k * 64, gi0);
+        }
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x, rs.next()) {
+          const int slot = rs.idx;
+          const int64_t tile = 2 * static_cast<int64_t>(c.t) + x;
+          mbar_wait(&bar->empty[slot], rs.ph ^ 1);
+          if (x == 0) TRACE(0, c.it, 0);
+          mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
+          uint8_t* dst = sm.slot(slot);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(dst + h * panel_t, &tmap_t, &bar->full[slot], static_cast<int32_t>(tile * TILE + h * 64), 0);
+          bulk_load_1d(sm.slot_labels(slot), p.labels + tile * TILE, META_LABEL_BYTES, &bar->full[slot]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            bulk_load_1d(sm.slot_stats(slot, k), p.row_stats + k * p.n_pad + tile * TILE, TILE * 4, &bar->full[slot]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp0) {
+    // ---- S issuer: S(k) = Z_I [Z_2k ; Z_2k+1]^T into the S pair, once the epilogue holds S(k - 1) in registers
+    const uint32_t a_base = smem_u32(sm.a_tile);
+    const int nk = p.dc * 4;
+    Ring ss(p.nslot);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next()) {
+      if (c.first()) mbar_wait_warp(&bar->a_full, c.seg & 1, lane);
+      const uint32_t s0 = ss.idx, ph0 = ss.ph;
+      ss.next();
+      const uint32_t s1 = ss.idx, ph1 = ss.ph;
+      ss.next();
+      mbar_wait_warp(&bar->full[s0], ph0, lane);
+      mbar_wait_warp(&bar->full[s1], ph1, lane);
+      if (c.it > 0) mbar_wait_warp(&bar->s_free, (c.it - 1) & 1, lane);
+      TRACE(1, c.it, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        // A = Z_I, K-major.  B = Z^T slot(s) read MN-major: 64-anchor MN atoms one panel apart (LBO), 8-row K (= d)
+        // groups 1024 B apart (SBO); each K = 16 step advances 16 rows of Z^T.
+        const uint32_t d_tmem = tmem_u + kSCol;
+        const uint32_t b0 = smem_u32(sm.slot(s0)), b1 = smem_u32(sm.slot(s1));
+        if (s1 == s0 + 1) {
+          constexpr uint32_t idesc2 = make_idesc_bf16(TILE, 2 * TILE, false, true);
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
+            mma_ss(d_tmem, make_smem_desc_sw128(a_base + pa, 16, 1024),
+                   make_smem_desc_sw128(b0 + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024), idesc2, kk != 0 ? 1u : 0u);
+          }
+        } else {
+          constexpr uint32_t idesc1 = make_idesc_bf16(TILE, TILE, false, true);
+          for (int x = 0; x < 2; ++x)
+            for (int kk = 0; kk < nk; ++kk) {
+              const uint32_t pa = static_cast<uint32_t>(kk >> 2) * CHUNK_BYTES + static_cast<uint32_t>(kk & 3) * 32;
+              mma_ss(d_tmem + x * TILE, make_smem_desc_sw128(a_base + pa, 16, 1024),
+                     make_smem_desc_sw128((x ? b1 : b0) + static_cast<uint32_t>(kk) * 2048u, panel_t, 1024), idesc1,
+                     kk != 0 ? 1u : 0u);
+            }
+        }
+        tc_commit(&bar->s_full);
+        if (c.last()) tc_commit(&bar->a_empty);               // only the S MMAs read the A tile
+      }
+      __syncwarp();
+      TRACE(1, c.it, 1);
+    }
+  } else if (warp == kMmaWarp1) {
+    // ---- T.Z issuer: dZ_I += T(tile) Z_tile, A = T from TMEM, B = the tile's Z^T slot read K-major
+    const uint32_t idesc_tz = make_idesc_bf16(TILE, p.d_pad, false, false);
+    Ring ts(p.nslot);
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next()) {
+      const bool first = c.first();
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x, ts.next()) {
+        mbar_wait_warp(&bar->t_full[x], c.it & 1, lane);
+        if (first && x == 0) mbar_wait_warp(&bar->dz_empty, (c.seg & 1) ^ 1, lane);
+        if (x == 0) TRACE(1, c.it, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_base = smem_u32(sm.slot(ts.idx));
+          const uint32_t a_tmem = tmem_u + kTCol + static_cast<uint32_t>(x) * 64u;
+#pragma unroll
+          for (int k = 0; k < TILE / 16; ++k) {
+            const uint64_t bd = make_smem_desc_sw128(b_base + static_cast<uint32_t>(k >> 2) * panel_t +
+                                                     static_cast<uint32_t>(k & 3) * 32u, 16, 1024);
+            mma_ts(tmem_u, a_tmem + k * 8, bd, idesc_tz, (first && x == 0 && k == 0) ? 0u : 1u);
+          }
+          tc_commit(&bar->empty[ts.idx]);
+          tc_commit(&bar->t_free[x]);
+          if (c.last() && x == 1) tc_commit(&bar->dz_full);
+        }
+        __syncwarp();
+        if (x == 1) TRACE(1, c.it, 3);
+      }
+    }
+  } else if (warp < kEpilogueWarps) {
+    const int wg = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const ExpK ek = make_expk<3>(p);
+    const float coef = p.grad_out[0] * p.scalars[3] * p.inv_tau;
+    int64_t gi0 = 0, gi = 0;
+    bool row_ok = false;
+    int li = 0;
+    float logD_i = 0.f, invc_i = 0.f, u_i = 0.f;
+    uint64_t uiui = 0ull;
+    int4 rsig = make_int4(0, 0, 0, 0);
+
+    Ring rs(p.nslot);
+    const uint32_t ct128 = static_cast<uint32_t>(p.CT128);
+    const uint32_t tail_jb = (p.N % TILE) ? ct128 - 1u : 0xffffffffu;
+    uint32_t row_jb = 0;
+    uint32_t apmask = 0;                                 // tiles of the group whose pairs are ALL positives
+    auto slow_mask = [&](uint32_t grp) -> uint32_t {
+      const uint32_t t = (grp << 5) + static_cast<uint32_t>(lane);
+      bool slow = true, ap = false;
+      if (t < ct128) {
+        const int4 cs = p.sig[t];
+        const bool edge = t == row_jb || t == tail_jb;
+        slow = edge || sig_overlap(rsig, cs);
+        ap = !edge && rsig.x == rsig.y && cs.x == cs.y && cs.x == rsig.x;
+      }
+      apmask = __ballot_sync(kFullMask, ap);
+      return __ballot_sync(kFullMask, slow);
+    };
+    uint32_t mask = 0, mask_grp = 0xffffffffu;
+    const int c0 = 2 * wg;                               // this warpgroup's two 32-column chunks of every tile
+    for (TileCursor c(f0, f1, p.CT); c.valid(); c.next()) {
+      if (c.first()) {
+        gi0 = p.row_begin + (I0 + c.seg) * TILE;
+        gi = gi0 + r;
+        row_jb = static_cast<uint32_t>(gi0 / TILE);
+        row_ok = gi < p.row_end;
+        li = row_ok ? p.labels[gi] : 0;
+        logD_i = row_ok ? p.row_stats[gi] : 0.f;
+        invc_i = row_ok ? p.row_stats[p.n_pad + gi] : 0.f;
+        u_i = row_ok ? p.row_stats[3 * p.n_pad + gi] : 0.f;
+        uiui = pack_f32x2(u_i, u_i);
+        rsig = p.sig[rb0 + I0 + c.seg];
+        mask_grp = 0xffffffffu;
+      }
+      const uint32_t par = c.it & 1u;
+      const uint32_t tile0 = 2u * c.t;                   // tiles tile0, tile0 + 1: the same group of 32
+      if ((tile0 >> 5) != mask_grp) {
+        mask_grp = tile0 >> 5;
+        mask = slow_mask(mask_grp);
+      }
+      TRACE(2 + warp, c.it, 3);
+      mbar_wait_warp(&bar->s_full, par, lane);
+      TRACE(2 + warp, c.it, 0);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(lane_base + kSCol + c0 * 32, va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int slot = rs.idx;
+        mbar_wait_warp(&bar->full[slot], rs.ph, lane);        // labels / statistics of the slot (complete long ago)
+        rs.next();
+        const uint32_t tile = tile0 + x;
+        const bool slow = ((mask >> (tile & 31)) & 1u) != 0u;
+        const bool allpos = ((apmask >> (tile & 31)) & 1u) != 0u;
+        const int64_t j0 = static_cast<int64_t>(tile) * TILE;
+        const int32_t* lab_s = sm.slot_labels(slot);
+        const float* logD_s = sm.slot_stats(slot, 0);
+        const float* invc_s = sm.slot_stats(slot, 1);
+        const float* u_s = sm.slot_stats(slot, 3);
+        const int64_t dj = gi - j0;
+        const int jdiag = (dj >= 0 && dj < TILE) ? static_cast<int>(dj) : -1;
+        const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
+        const uint32_t s_addr = lane_base + kSCol + x * TILE + c0 * 32;
+        const uint32_t t_addr = lane_base + kTCol + x * 64 + c0 * 16;
+        // va holds chunk c0 of this tile.  The chunk after it is loaded under its arithmetic, and under the second
+        // chunk's arithmetic the first chunk of the NEXT tile of the pair.
+        auto run_half = [&](auto&& chunk_body) {
+          uint32_t pk[16];
+          tmem_ld_32x32b_x32(s_addr + 32, vb);
+          chunk_body(va, c0, pk);
+          tmem_wait_ld();
+          if (x == 1) {                                        // every S column of the pair is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar->s_free);
+            TRACE(2 + warp, c.it, 2);
+          }
+          if (c.it > 0) mbar_wait_warp(&bar->t_free[x], par ^ 1u, lane);   // T.Z of the previous pair's tile x is done
+          tmem_st_32x32b_x16(t_addr, pk);
+          if (x == 0) tmem_ld_32x32b_x32(s_addr + TILE, va);
+          chunk_body(vb, c0 + 1, pk);
+          if (x == 0) tmem_wait_ld();
+          tmem_st_32x32b_x16(t_addr + 16, pk);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar->t_full[x]);
+          if (x == 1) TRACE(2 + warp, c.it, 1);
+        };
+        if (!slow) {
+          run_half([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
+            bwd_chunk_fast_swp(cur, smem_u32(u_s + ch * 32), ek, uiui, pk);
+          });
+        } else if (allpos && row_ok) {
+          run_half([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
+            bwd_chunk_allpos<MODE>(cur, logD_s + ch * 32, invc_s + ch * 32, u_s + ch * 32, ek, p, logD_i, invc_i, uiui, pk);
+          });
+        } else {
+          run_half([&](const uint32_t(&cur)[32], int ch, uint32_t(&pk)[16]) {
+            bwd_chunk_slow<MODE>(cur, ch, jdiag, jmax, li, lab_s, logD_s, invc_s, u_s, p, logD_i, invc_i, u_i, pk);
+          });
+        }
+      }
+
+      if (c.last()) {
+        // ---- drain dZ_I for this row-block segment: TMEM -> scale -> global accumulate ----
+        mbar_wait_warp(&bar->dz_full, c.seg & 1, lane);
+        tc_fence_after();
+        const int half = p.d_pad >> 1;
+        float* out = p.dz + (gi - p.row_begin) * p.lddz;
+        for (int cc = wg * half; cc < (wg + 1) * half; cc += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_base + cc, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int col = cc + e;
               if (col < p.d) atomicAdd(out + col, __uint_as_float(v[e]) * coef);
             }
           }
@@ -1969,6 +2307,21 @@ static bool sym_enabled() {
   return env != 0 && !(g_dbg & 64);
 }
 
+// SPCL_BWD_WIDE=0/1 overrides the default choice of the backward kernel (bwd_wide_kernel: 128 x 256 S tiles).
+// Off by default: measured 540 us against 458 us for bwd_kernel at cfg3 (profiles/r02zb_bwd_wide_experiment.txt) --
+// with one S buffer the S product and the epilogue run in series, and the epilogue, not the MMA, bounds the backward.
+#ifndef SPCL_BWD_WIDE_DEFAULT
+#define SPCL_BWD_WIDE_DEFAULT 0
+#endif
+static bool wide_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("SPCL_BWD_WIDE");
+    env = (e == nullptr) ? SPCL_BWD_WIDE_DEFAULT : (e[0] != '0');
+  }
+  return (env != 0 || (g_dbg & 16384)) && !(g_dbg & 32);      // debug flag 16384 selects it at run time (tests)
+}
+
 static bool wg3_enabled() {
   static int env = -1;
   if (env < 0) {
@@ -2251,8 +2604,14 @@ extern "C" int spcl_supcon_bwd_bf16(const void* zb, int64_t n_total, int64_t n_p
     }
   }
   const size_t smem = tc::smem_payload_bytes(p.dc, p.nslot, 128, true) + 1024;
-  auto kern = mode == SPCL_MODE_SOFT ? tc::bwd_kernel<SPCL_MODE_SOFT>
-              : mode == SPCL_MODE_HARD ? tc::bwd_kernel<SPCL_MODE_HARD> : tc::bwd_kernel<SPCL_MODE_NONE>;
+  // 128 x 256 S tiles: d_pad <= 128 (TMEM: dZ 128 + S pair 256 + T 128 columns), an even number of column tiles and
+  // a slot ring that holds two pairs
+  const bool wide = d_pad <= 128 && p.CT128 % 2 == 0 && p.nslot >= 4 && tc::wide_enabled();
+  if (wide) p.CT = p.CT128 / 2;                          // pairs of column tiles
+  auto kern = wide ? (mode == SPCL_MODE_SOFT ? tc::bwd_wide_kernel<SPCL_MODE_SOFT>
+                      : mode == SPCL_MODE_HARD ? tc::bwd_wide_kernel<SPCL_MODE_HARD> : tc::bwd_wide_kernel<SPCL_MODE_NONE>)
+              : (mode == SPCL_MODE_SOFT ? tc::bwd_kernel<SPCL_MODE_SOFT>
+                 : mode == SPCL_MODE_HARD ? tc::bwd_kernel<SPCL_MODE_HARD> : tc::bwd_kernel<SPCL_MODE_NONE>);
   rc = tc::set_smem(kern, smem);
   if (rc != SPCL_OK) return rc;
   CUtensorMap tmap_t;

@@ -663,3 +663,32 @@ def test_all_positive_tiles_against_the_oracle(mode, gamma, cg):
             assert np.isclose(res["ratio"], ref["ratio"], rtol=3e-4), (run, res["ratio"], ref["ratio"])
         rel, cos = _grad_metrics(res, ref)
         assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (run, rel, cos)
+
+
+@pytest.mark.parametrize("n,run,mode,gamma", [(1024, 256, "soft", 6.0), (1024, 96, "hard", 5.5), (1536, 1, "none", 1e6),
+                                              (4096, 1, "soft", 8.0)])
+def test_wide_backward_kernel_against_the_oracle(n, run, mode, gamma):
+    """`bwd_wide_kernel` (128 x 256 S tiles, opt-in: SPCL_BWD_WIDE=1 / debug flag 16384; see
+    profiles/r02zb_bwd_wide_experiment.txt) against the fp64 oracle, same tolerances as the default backward:
+    all-positive, mixed and SimCLR labellings; 2 n / 128 column tiles = 16 ... 64 (pairs that wrap the slot ring
+    included: the ring holds five tiles)."""
+    import ctypes
+    h = nat.lib()
+    h.spcl_debug_set_flags.argtypes = [ctypes.c_int]
+    d = 128
+    labels = (torch.arange(n) // run)
+    z1, z2 = make_views(labels, d, sigma=0.7, seed=11)
+    z1, z2 = z1.bfloat16().float(), z2.bfloat16().float()
+    cls = "SupConLoss1" if mode == "none" else "SP"
+    h.spcl_debug_set_flags(16384)
+    try:
+        res = _run(z1, z2, cls=cls, target=labels.int().numpy(), gamma=gamma, mode=mode, precision="bf16", validate=False)
+    finally:
+        h.spcl_debug_set_flags(0)
+    base = _run(z1, z2, cls=cls, target=labels.int().numpy(), gamma=gamma, mode=mode, precision="bf16", validate=False)
+    ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=gamma, mode=mode)
+    rel, cos = _grad_metrics(res, ref)
+    assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (rel, cos)
+    # the two backward kernels evaluate the same T (same epilogue code) and differ only in accumulation order
+    g, b = np.concatenate([res["dz1"], res["dz2"]]), np.concatenate([base["dz1"], base["dz2"]])
+    assert np.abs(g - b).max() <= 2e-3 * np.abs(b).max(), np.abs(g - b).max() / np.abs(b).max()

@@ -1,6 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "bf16 or cfg3 or positive or stats_parts" 2>&1 | tail -2
-for V in notry cur tryw notry cur; do
-  if [ $V == cur ]; then unset SPCL_B200_LIB; else export SPCL_B200_LIB=$PWD/variants/$V.so; fi
-  python tools/gpu_time.py 16384 128 self
-done
-unset SPCL_B200_LIB; python tools/gpu_time.py 16384 128 slice
+timeout 120 tools/mma_bench.bin 2>&1 | tee gpurun_out/r02zb_mma_bench.txt
+SPCL_B200_LIB=$PWD/variants/trace.so timeout 300 python tools/gpu_trace.py 16384 128 0 both 2>&1 | sed -n "/bwd_kernel/,\$p" > gpurun_out/r02zb_trace_wide.log; sed -n 1,3p gpurun_out/r02zb_trace_wide.log; sed -n 20,30p gpurun_out/r02zb_trace_wide.log

@@ -72,7 +72,7 @@ def main():
     torch.cuda.synchronize()
     h.spcl_debug_set_trace(None)
     h.spcl_debug_set_flags(0)
-    dump(f"bwd_kernel flags={bwd_flags}", tr, ntiles=40)
+    dump(f"bwd_kernel flags={bwd_flags}", tr, ntiles=40, both=len(sys.argv) > 4)
 
 
 if __name__ == "__main__":

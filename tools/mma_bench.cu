@@ -14,6 +14,8 @@ constexpr int COUNT = 256;
 
 // variant: 0 SS N128 | 1 SS N256 | 2 TS N128 | 3 TS N256 | 4 SS N128, two D buffers alternating
 //          5 TS N128 with B read MN-major | 6 SS N64 | 7 SS N128 with B read MN-major
+//          8 SS N128, A read MN-major | 9 SS N128, A and B read MN-major | 10 SS N256, A read MN-major
+//          11 SS N256, B read MN-major (4 atoms of 64, one panel apart)
 __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -33,8 +35,8 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, uns
   const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 32768);
   unsigned long long t0 = 0, t1 = 0;
   if (warp == 1) {
-    const int n = (variant == 1 || variant == 3) ? 256 : (variant == 6 ? 64 : 128);
-    const uint32_t idesc = make_idesc_bf16(128, n, false, variant == 5 || variant == 7);
+    const int n = (variant == 1 || variant == 3 || variant == 10 || variant == 11) ? 256 : (variant == 6 ? 64 : 128);
+    const uint32_t idesc = make_idesc_bf16(128, n, variant >= 8 && variant <= 10, variant == 5 || variant == 7 || variant == 9 || variant == 11);
     const uint32_t b_panel = (n == 256) ? 32768u : 16384u;
     __syncwarp();
     t0 = clock64();
@@ -48,6 +50,15 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int ldtm_noise, uns
           mma_ts(d, tmem + 256 + kk * 8, make_smem_desc_sw128(b_base + off_b, 16, 1024), idesc, i != 0);
         } else if (variant == 5) {
           mma_ts(d, tmem + 256 + kk * 8, make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024), idesc, i != 0);
+        } else if (variant == 11) {
+          mma_ss(d, make_smem_desc_sw128(a_base + off_a, 16, 1024), make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024),
+                 idesc, i != 0);
+        } else if (variant >= 8) {
+          // A read MN-major: 2 panels of 128 k-rows x 64 rows of M (128 B), K = 16 step = 16 k-rows = 2048 B
+          const uint64_t ad = make_smem_desc_sw128(a_base + kk * 2048, 16384, 1024);
+          const uint64_t bd = variant == 9 ? make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024)
+                                           : make_smem_desc_sw128(b_base + off_b, 16, 1024);
+          mma_ss(d, ad, bd, idesc, i != 0);
         } else if (variant == 7) {
           mma_ss(d, make_smem_desc_sw128(a_base + off_a, 16, 1024), make_smem_desc_sw128(b_base + kk * 2048, 16384, 1024),
                  idesc, i != 0);
@@ -87,10 +98,12 @@ int main() {
   const size_t smem = 32768 + 65536 + 1024;
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const char* names[] = {"SS M128 N128", "SS M128 N256", "TS M128 N128", "TS M128 N256", "SS N128 two D buffers",
-                         "TS N128, B MN-major", "SS M128 N64", "SS N128, B MN-major"};
-  for (int noise : {0, 4000}) {
-    for (int grid : {1, 148}) {
-      for (int v = 0; v < 8; ++v) {
+                         "TS N128, B MN-major", "SS M128 N64", "SS N128, B MN-major", "SS N128, A MN-major",
+                         "SS N128, A+B MN-major", "SS N256, A MN-major",
+                         "SS N256, B MN-major"};
+  for (int noise : {0}) {
+    for (int grid : {148}) {
+      for (int v = 0; v < 12; ++v) {
         bench<<<grid, 128, smem>>>(v, noise, d_out);
         bench<<<grid, 128, smem>>>(v, noise, d_out);
         cudaError_t e = cudaDeviceSynchronize();
