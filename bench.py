@@ -644,9 +644,26 @@ def main():
             torch.cuda.synchronize()
             return (time.perf_counter() - t0) / 100 * 1e6
         small = {"workload": "cfg2: 3 meta-label problems, N = 512, d = 256, fp32 path, fwd+bwd of all three",
+                 "route": "one cooperative launch per loss call / per group (spcl_supcon_group_fused_f32): S kept in "
+                          "registers across the stages, backward = one multiply",
                  "eager_us_per_step": small_step(False), "cuda_graph_us_per_step": small_step(True),
                  "grouped_launch_us_per_step": small_step(False, grouped=True),
                  "grouped_graph_us_per_step": small_step(False, grouped=True, group_graph=True)}
+        try:                                        # device time of the group through the C ABI alone
+            import importlib.util
+            gs_spec = importlib.util.spec_from_file_location("gpu_small", os.path.join(os.path.dirname(
+                os.path.abspath(__file__)), "tools", "gpu_small.py"))
+            gs = importlib.util.module_from_spec(gs_spec)
+            gs_spec.loader.exec_module(gs)
+            small["c_abi_device_us"] = gs.raw_group_times(256, 256)
+        except Exception as e:                      # noqa: BLE001
+            small["c_abi_device_us"] = {"error": f"{type(e).__name__}: {e}"}
+        os.environ["SPCL_FUSED_SMALL"] = "0"        # the staged route (one launch per stage), same harness
+        try:
+            small["staged_route"] = {"eager_us_per_step": small_step(False), "cuda_graph_us_per_step": small_step(True),
+                                     "grouped_launch_us_per_step": small_step(False, grouped=True)}
+        finally:
+            del os.environ["SPCL_FUSED_SMALL"]
 
     # ---------------- dense front end, secondary figure: HBM-bound kernels ----------------
     dense_fe = None

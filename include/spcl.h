@@ -257,6 +257,17 @@ typedef struct spcl_problem_f32 {
 int spcl_supcon_group_fwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream);
 int spcl_supcon_group_bwd_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream);
 
+/* One COOPERATIVE launch for the forward and the backward of the group: writes row_stats, scalars and dz for an
+ * upstream gradient d(total)/d(loss) = 1 (the loss is a scalar: the caller scales dz; grad_out is not read).  Every
+ * 64 x 64 tile of every problem is one CTA and all of them must be resident at once:
+ * max_k ceil(n_total_k / 64)^2 * count <= spcl_supcon_fused_capacity() (CTAs, for the current device; 0 where
+ * cooperative launches are unavailable), else SPCL_ERR_UNSUPPORTED and nothing is launched -- use the two calls above.
+ * This is the path of the reference's own batch sizes (semi_seg/hooks/infonce.py:182: 2 x batch <= 512 anchors, three
+ * meta-label problems per step): S is formed once and kept in registers across the stages of
+ * contrast_loss3.py:147-205 and its autograd backward. */
+int spcl_supcon_fused_capacity(void);
+int spcl_supcon_group_fused_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream);
+
 /* ---- scalar epilogue (after the optional all-reduce of partials) ------------------------------
  * scalars = { loss, ratio, scale, scale / N }; scale = 1/ratio if correct_grad and ratio > 0
  * (contrast_loss3.py:189-201).  A NaN loss is reported by the host wrapper as RuntimeError (:203). */

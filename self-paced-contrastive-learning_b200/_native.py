@@ -59,6 +59,7 @@ SIGNATURES = {
     "spcl_supcon_finalize": [_ptr, _i64, _c.c_int, _ptr, _ptr],
     "spcl_supcon_group_fwd_f32": [_ptr, _c.c_int, _ptr],
     "spcl_supcon_group_bwd_f32": [_ptr, _c.c_int, _ptr],
+    "spcl_supcon_group_fused_f32": [_ptr, _c.c_int, _ptr],
 }
 MAX_GROUP = 8
 
@@ -69,7 +70,8 @@ class ProblemF32(_c.Structure):
                 ("inv_tau", _f32), ("gamma", _f32), ("mode", _c.c_int), ("correct_grad", _c.c_int),
                 ("acc", _ptr), ("row_stats", _ptr), ("stats_stride", _i64), ("partials", _ptr), ("scalars", _ptr),
                 ("grad_out", _ptr), ("dz", _ptr), ("lddz", _i64)]
-OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error", "spcl_workspace_bytes")
+OTHER_SYMBOLS = ("spcl_version", "spcl_error_string", "spcl_last_cuda_error", "spcl_workspace_bytes",
+                 "spcl_supcon_fused_capacity")
 WS_ZB, WS_LABELS, WS_SIG, WS_ACC, WS_ROW_STATS, WS_PARTIALS, WS_SCALARS, WS_BWD_ZT = range(8)
 ALL_SYMBOLS = tuple(SIGNATURES) + OTHER_SYMBOLS
 
@@ -114,6 +116,7 @@ def lib() -> ctypes.CDLL:
                 handle.spcl_error_string.argtypes = [_c.c_int]
                 handle.spcl_error_string.restype = _c.c_char_p
                 handle.spcl_last_cuda_error.restype = _c.c_char_p
+                handle.spcl_supcon_fused_capacity.restype = _c.c_int
                 _lib = handle
     return _lib
 

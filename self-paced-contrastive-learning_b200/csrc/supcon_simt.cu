@@ -14,6 +14,11 @@
 //   backward: one CTA owns 64 anchor rows; per column tile it forms
 //             T_ij = M_ij E_ij u_i - P_ij W_ij / c_i  +  (same with i <-> j)
 //             in shared memory and accumulates dZ_I += T_IJ Z_J in registers.
+#include <cooperative_groups.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spcl {
@@ -823,6 +828,280 @@ __global__ void finalize_kernel(const float* __restrict__ partials, float n_tota
   finalize_body(partials, n_total, correct_grad, scalars);
 }
 
+// =================================================================================================
+// One launch for forward AND backward of K small label-form problems (the reference's own batch sizes: N = 2 x 30 ..
+// 2 x 256 anchors, K = 3 meta-label losses per encoder step).
+// =================================================================================================
+// Every 64 x 64 tile of every problem is one CTA of a cooperative grid (all CTAs co-resident); the tile's 16
+// similarities per thread stay in REGISTERS across the grid-wide barriers, so S is formed once instead of three times
+// and nothing but 16 B of row sums per anchor passes through memory between the stages:
+//   0  zero acc / partials / dz                                                         | grid sync
+//   1  S tile, partial rowsum / c / sum P <z_i, z_j> -> atomics into acc                 | grid sync
+//   2  (self-paced modes) W from the complete logD_i, partial sum P W LLH / sum P W      | grid sync
+//   3  row_stats planes + the three partial sums of the loss (CTAs of tile column 0)    | grid sync
+//   4  scalars; T tile from the same registers; dZ_I += T_IJ Z_J -> atomics into dz, scaled for an upstream gradient 1
+// The loss is a scalar, so the caller's backward is dz * d(total)/d(loss): no second launch at all.
+// Same per-pair arithmetic as fwd_split_body / bwd_split_body.
+namespace cg = cooperative_groups;
+#ifndef SPCL_FUSED_STAMP
+#define SPCL_FUSED_STAMP 0
+#endif
+
+__device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(NT, 2) fused_group_kernel(const __grid_constant__ Group g, int flags) {
+  const int any_sp = flags & 1;
+#if SPCL_FUSED_STAMP              // development build: phase times of CTA 0 (tools/gpu_small.py with a -DSPCL_FUSED_STAMP=1 library)
+  const bool stamp = (flags & 2) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  long long tq[6] = {0, 0, 0, 0, 0, 0};
+#define FSTAMP(i) do { if (stamp) tq[i] = clock64(); } while (0)
+#else
+#define FSTAMP(i) do { } while (0)
+#endif
+  FSTAMP(0);
+  cg::grid_group grid = cg::this_grid();
+  __shared__ Smem sm;
+  __shared__ float ts[BM][BN + 1];
+  __shared__ float rstat[3][BM], cstat[3][BN];          // logD | 1/c | u of the tile's rows / columns
+  __shared__ float red[3][2];
+  const int k = blockIdx.z;
+  const Args& p = g.p[k];
+  const bool active = blockIdx.x < g.gx[k] && blockIdx.y < g.gy[k];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * BM, j0 = static_cast<int64_t>(blockIdx.y) * BN;
+  float4* acc = g.acc[k];
+  float* partials = g.partials[k];
+  float* dz = g.dz[k];
+  const int64_t lddz = g.lddz[k];
+  const float shift = p.inv_tau;
+
+  // ---- 0: zero the accumulators of problem k (all CTAs of its z-slice take part)
+  {
+    const int64_t nthr = static_cast<int64_t>(gridDim.x) * gridDim.y * NT;
+    const int64_t t0 = (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * NT + tid;
+    for (int64_t t = t0; t < p.N; t += nthr) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t ndz = p.N * lddz;
+    for (int64_t t = t0; t < ndz; t += nthr) dz[t] = 0.f;
+    if (t0 < 3) partials[t0] = 0.f;
+  }
+  grid.sync();
+  FSTAMP(1);
+
+  // ---- 1: S tile + pass-A partial sums
+  int64_t gi[4], gj[4];
+  int li[4], lj[4];
+  float d[4][4];
+  if (active) {
+    split_rows(p, i0, ty, gi, li);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      gj[b] = j0 + tx + 16 * b;
+      lj[b] = gj[b] < p.N ? p.labels[gj[b]] : 0;
+    }
+    tile_dot(p, sm, i0, j0, d);
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (gj[b] >= p.N) continue;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (gi[a] == gj[b] || gi[a] >= p.N) continue;
+        s0[a] += expf(d[a][b] * p.inv_tau - shift);
+        if (li[a] == lj[b]) {
+          s1[a] += 1.f;
+          s2[a] += d[a][b];
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float r0 = row_sum16(s0[a]), r1 = row_sum16(s1[a]), r2 = row_sum16(s2[a]);
+      if (tx != 0 || gi[a] >= p.N) continue;
+      float* out = reinterpret_cast<float*>(acc + gi[a]);
+      if (r0 != 0.f) atomicAdd(out + 0, r0);
+      if (r1 != 0.f) atomicAdd(out + 1, r1);
+      if (p.mode == SPCL_MODE_NONE && r2 != 0.f) atomicAdd(out + 2, r2);
+    }
+  }
+  grid.sync();
+  FSTAMP(2);
+
+  // ---- 2: self-paced sums (W needs the complete logD_i)
+  if (any_sp) {
+    if (active && p.mode != SPCL_MODE_NONE) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (gi[a] >= p.N) continue;
+        const float logD = shift + logf(ldcg4(acc + gi[a]).x);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (gj[b] >= p.N || gi[a] == gj[b] || li[a] != lj[b]) continue;
+          const float llh = d[a][b] * p.inv_tau - logD;
+          const float w = sp_weight(-llh, p.gamma, p.inv_gamma, p.mode);
+          s0[a] = fmaf(w, llh, s0[a]);
+          s1[a] += w;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float r0 = row_sum16(s0[a]), r1 = row_sum16(s1[a]);
+        if (tx != 0 || gi[a] >= p.N || r1 == 0.f) continue;
+        float* out = reinterpret_cast<float*>(acc + gi[a]);
+        atomicAdd(out + 2, r0);
+        atomicAdd(out + 3, r1);
+      }
+    }
+    grid.sync();
+  }
+
+  FSTAMP(3);
+  // ---- 3: per-row epilogue (row_stats planes for the caller) + the loss' three partial sums
+  if (active && blockIdx.y == 0) {
+    float l = 0.f, w = 0.f, c = 0.f;
+    const int64_t r = i0 + tid;
+    if (tid < BM && r < p.N) {
+      const float4 a = ldcg4(acc + r);
+      const float logD = shift + logf(a.x);
+      const float cnt = a.y;
+      const float wl = p.mode == SPCL_MODE_NONE ? a.z * p.inv_tau - cnt * logD : a.z;
+      const float wp = p.mode == SPCL_MODE_NONE ? cnt : a.w;
+      const float invc = 1.f / cnt;                    // c == 0 -> inf -> NaN loss, like the reference's 0/0
+      const float A = wp * invc;
+      float* rs = g.row_stats[k];
+      const int64_t sld = g.sld[k];
+      rs[r] = logD;
+      rs[sld + r] = invc;
+      rs[2 * sld + r] = A;
+      rs[3 * sld + r] = A / a.x;
+      l = wl * invc;
+      w = wp;
+      c = cnt;
+    }
+    if (tid < BM) {                                    // warps 0 and 1
+      l = warp_sum(l);
+      w = warp_sum(w);
+      c = warp_sum(c);
+      if ((tid & 31) == 0) { red[0][tid >> 5] = l; red[1][tid >> 5] = w; red[2][tid >> 5] = c; }
+    }
+    __syncthreads();
+    if (tid < 3) atomicAdd(&partials[tid], red[tid][0] + red[tid][1]);
+  }
+  grid.sync();
+  FSTAMP(4);
+
+  // ---- 4: scalars, T tile, dZ
+  if (!active) return;
+  const float loss_sum = __ldcg(partials + 0), wpt = __ldcg(partials + 1), pct = __ldcg(partials + 2);
+  const float n_total = static_cast<float>(p.N);
+  const float ratio = wpt / pct;                       // 0/0 -> NaN, like mean() of an empty selection (:189)
+  const float scale = (g.correct_grad[k] && ratio > 0.f) ? 1.f / ratio : 1.f;   // :199-201
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    float* sc = g.scalars[k];
+    sc[0] = -(loss_sum / n_total) * scale;             // :197
+    sc[1] = ratio;
+    sc[2] = scale;
+    sc[3] = scale / n_total;
+  }
+  if (tid < BM + BN) {
+    const bool row = tid < BM;
+    const int q = row ? tid : tid - BM;
+    const int64_t idx = (row ? i0 : j0) + q;
+    float logD = 0.f, invc = 0.f, u = 0.f;
+    if (idx < p.N) {
+      const float4 a = ldcg4(acc + idx);
+      logD = shift + logf(a.x);
+      invc = 1.f / a.y;
+      u = (p.mode == SPCL_MODE_NONE ? a.y : a.w) * invc / a.x;
+    }
+    float (*st)[BM] = row ? rstat : cstat;
+    st[0][q] = logD;
+    st[1][q] = invc;
+    st[2][q] = u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int cj = tx + 16 * b;
+    const float ldj = cstat[0][cj], icj = cstat[1][cj], uj = cstat[2][cj];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int ri = ty * 4 + a;
+      float tv = 0.f;
+      if (gj[b] < p.N && gi[a] < p.N && gi[a] != gj[b]) {
+        const float s = d[a][b] * p.inv_tau;
+        tv = expf(s - shift) * (rstat[2][ri] + uj);
+        if (li[a] == lj[b])
+          tv -= sp_weight(rstat[0][ri] - s, p.gamma, p.inv_gamma, p.mode) * rstat[1][ri] +
+                sp_weight(ldj - s, p.gamma, p.inv_gamma, p.mode) * icj;
+      }
+      ts[ri][cj] = tv;
+    }
+  }
+  __syncthreads();
+  const float coef = scale / n_total * p.inv_tau;      // upstream gradient 1
+  const int jmax = static_cast<int>(min(static_cast<int64_t>(BN), p.N - j0));
+  for (int c0 = 0; c0 < p.d; c0 += 128) {              // 8 columns per thread and pass: dzacc stays in 32 registers
+    float dzacc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dzacc[a][c] = 0.f;
+#pragma unroll 4
+    for (int jj = 0; jj < jmax; ++jj) {
+      const float* zrow = p.z + (j0 + jj) * p.ldz + c0;
+      float tv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) tv[a] = ts[ty * 4 + a][jj];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = tx + 16 * c;
+        const float zv = (c0 + col) < p.d ? zrow[col] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dzacc[a][c] = fmaf(tv[a], zv, dzacc[a][c]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (gi[a] >= p.N) continue;
+      float* out = dz + gi[a] * lddz + c0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = tx + 16 * c;
+        if (c0 + col < p.d) atomicAdd(out + col, dzacc[a][c] * coef);
+      }
+    }
+  }
+#if SPCL_FUSED_STAMP
+  if (stamp) {
+    tq[5] = clock64();
+    printf("spcl fused_group_kernel (CTA 0, cycles): zero+sync %lld | S+stats+sync %lld | sp+sync %lld | rows+sync %lld | T+dZ %lld\n",
+           tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4]);
+  }
+#endif
+#undef FSTAMP
+}
+
+// CTAs of fused_group_kernel that can be resident at once on the current device (0: cooperative launch unsupported)
+static int fused_capacity() {
+  constexpr int kMaxDev = 64;
+  static int cap[kMaxDev];
+  static bool known[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 0;
+  if (!known[dev]) {
+    int coop = 0, sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (coop == 0 || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_group_kernel, NT, 0) != cudaSuccess)
+      per_sm = 0;
+    (void)cudaGetLastError();
+    cap[dev] = per_sm * sms;
+    known[dev] = true;
+  }
+  return cap[dev];
+}
+
 static int check_common(const float* z, int64_t n_total, int32_t d, int64_t ldz, const int32_t* labels,
                         const uint8_t* tri, int64_t n_half, int64_t row_begin, int64_t row_end, float inv_tau,
                         float gamma, int mode) {
@@ -1058,5 +1337,31 @@ extern "C" int spcl_supcon_group_bwd_f32(const spcl_problem_f32* problems, int c
   else if (dmax <= 128) simt::bwd_split_group_kernel<8><<<grid, simt::NT, 0, s>>>(g);
   else simt::bwd_split_group_kernel<16><<<grid, simt::NT, 0, s>>>(g);
   SPCL_LAUNCH_CHECK("spcl_supcon_group_bwd_f32");
+  return SPCL_OK;
+}
+
+// ---- one cooperative launch: forward (row_stats, scalars) AND dz for an upstream gradient of 1 ------------------
+extern "C" int spcl_supcon_fused_capacity(void) { return simt::fused_capacity(); }
+
+extern "C" int spcl_supcon_group_fused_f32(const spcl_problem_f32* problems, int count, spcl_stream_t stream) {
+  simt::Group g{};
+  unsigned gx, gy; int dmax; bool any_sp; int64_t nmax;
+  int rc = fill_group(problems, count, false, g, gx, gy, dmax, any_sp, nmax);
+  if (rc != SPCL_OK) return rc;
+  gx = gy = 1;
+  for (int k = 0; k < count; ++k) {
+    if (problems[k].dz == nullptr || problems[k].lddz < problems[k].d) return SPCL_ERR_INVALID_ARG;
+    g.sp[k] = simt::Split{1};
+    g.gy[k] = static_cast<unsigned>(ceil_div(problems[k].n_total, static_cast<int64_t>(simt::BN)));
+    if (g.gx[k] > gx) gx = g.gx[k];
+    if (g.gy[k] > gy) gy = g.gy[k];
+  }
+  const int64_t ctas = static_cast<int64_t>(gx) * gy * count;
+  if (ctas > simt::fused_capacity()) return SPCL_ERR_UNSUPPORTED;     // the grid-wide barrier needs every CTA resident
+  int sp = (any_sp ? 1 : 0) | (std::getenv("SPCL_FUSED_STAMP") != nullptr ? 2 : 0);   // debug: phase times of CTA 0
+  void* args[] = {&g, &sp};
+  SPCL_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(simt::fused_group_kernel),
+                                            dim3(gx, gy, static_cast<unsigned>(count)), dim3(simt::NT), args, 0,
+                                            static_cast<cudaStream_t>(stream)));
   return SPCL_OK;
 }

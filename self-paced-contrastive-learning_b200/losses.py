@@ -241,10 +241,13 @@ class _FusedSupConBase(nn.Module):
         loss, scalars, aux = supcon_loss(proj_feat1, proj_feat2, target=target, mask=mask, temperature=self._t,
                                          gamma=gamma, mode=mode, correct_grad=cg, precision=self._precision,
                                          graph_cache=self._graphs)
-        self._scalars = scalars.detach()
-        self._ratio_cache = None
-        self._diag = _Diagnostics(proj_feat1, proj_feat2, aux["labels"], aux["tri"], aux["row_stats"], self._t,
-                                  gamma, mode)
+        # (plain attributes: nn.Module.__setattr__ checks every assignment against parameters / buffers / modules,
+        # ~5 us each on the host -- more than a kernel launch at the reference's batch sizes)
+        state = self.__dict__
+        state["_scalars"] = scalars.detach()
+        state["_ratio_cache"] = None
+        state["_diag"] = _Diagnostics(proj_feat1, proj_feat2, aux["labels"], aux["tri"], aux["row_stats"], self._t,
+                                      gamma, mode)
         if self._check_nan and torch.isnan(loss):      # :203-204 (one host sync, as in the reference)
             raise RuntimeError(loss)
         return loss
@@ -484,7 +487,7 @@ def grouped_forward(criteria, feats, targets=None, cuda_graph: bool = False):
     for (z1, _), t in zip(feats, targets):
         n, dev = z1.shape[0], z1.device
         lab = ops.label_codes(t, n, dev) if t is not None else torch.arange(n, dtype=torch.int32, device=dev)
-        labels.append(lab if cuda_graph else lab.repeat(2))
+        labels.append(lab if cuda_graph else torch.cat([lab, lab]))
     if cuda_graph:
         shapes = [tuple(z1.shape) for z1, _ in feats]
         key = (str(feats[0][0].device), tuple(shapes), tuple((float(t), float(g), int(m), bool(c)) for t, g, m, c in metas))
@@ -498,7 +501,8 @@ def grouped_forward(criteria, feats, targets=None, cuda_graph: bool = False):
         scalars = ops.supcon_group_f32(list(feats), labels, metas)
     out = []
     for crit, sc in zip(criteria, scalars):
-        crit._scalars, crit._ratio_cache, crit._diag = sc.detach(), None, None
+        state = crit.__dict__                    # (plain attributes, see forward)
+        state["_scalars"], state["_ratio_cache"], state["_diag"] = sc.detach(), None, None
         loss = sc[0]
         if crit._check_nan and torch.isnan(loss):
             raise RuntimeError(loss)

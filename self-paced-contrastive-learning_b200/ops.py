@@ -27,7 +27,9 @@ def _ptr(t: Optional[Tensor]):
 
 
 def _stream(t: Tensor):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    # (the raw-handle query: torch.cuda.current_stream() builds a Stream object, ~10 us per call on the host)
+    idx = t.device.index
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if idx is None else idx))
 
 
 def pad_to(x: int, m: int) -> int:
@@ -259,6 +261,72 @@ def _supcon_backward(ctx, g_scalars, g_stats, g_zpack, g_labels, g_sig):
 supcon_fwd.register_autograd(_supcon_backward, setup_context=_supcon_setup)
 
 
+# --------------------------------------------------------------------------------------------------
+# one cooperative launch for forward + backward at the reference's own batch sizes (spcl_supcon_group_fused_f32)
+# --------------------------------------------------------------------------------------------------
+_FUSED_CAP = {}
+
+
+def fused_capacity(device) -> int:
+    """CTAs of the fused small-batch kernel that can be co-resident on ``device`` (cached per device)."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _FUSED_CAP:
+        with torch.cuda.device(idx):
+            _FUSED_CAP[idx] = int(nat.lib().spcl_supcon_fused_capacity())
+    return _FUSED_CAP[idx]
+
+
+def fused_fits(shapes, device) -> bool:
+    """True when the K problems of ``shapes`` = [(n, d), ...] (2n anchors each) run as ONE cooperative launch: every
+    64 x 64 tile is a CTA and all must be resident.  SPCL_FUSED_SMALL=0 switches the route off (A/B, tests of the
+    multi-launch path)."""
+    if os.environ.get("SPCL_FUSED_SMALL", "1") == "0" or not shapes:
+        return False
+    tiles = max((2 * n + 63) // 64 for n, _ in shapes)
+    return tiles * tiles * len(shapes) <= fused_capacity(device)
+
+
+def _fused_problem(q, z, labels2, N, d, temperature, gamma, mode, correct_grad, ws, dz):
+    """Fill one ``spcl_problem_f32`` from the workspace ``ws`` = acc [N,4] | row_stats [4,N] | partials [4] | scalars [4]."""
+    q.z, q.n_total, q.d, q.ldz, q.labels = z.data_ptr(), N, d, z.stride(0), labels2.data_ptr()
+    q.inv_tau, q.gamma, q.mode, q.correct_grad = 1.0 / float(temperature), float(gamma), int(mode), int(bool(correct_grad))
+    base = ws.data_ptr()                               # (pointer arithmetic: a tensor slice costs ~3 us on the host)
+    q.acc, q.row_stats, q.stats_stride = base, base + N * 16, N
+    q.partials, q.scalars = base + N * 32, base + N * 32 + 16
+    q.dz, q.lddz = dz.data_ptr(), dz.stride(0)
+
+
+class _FusedSupCon(torch.autograd.Function):
+    """One fp32 label-form problem on the fused kernel: the forward call also produces dz for an upstream gradient of
+    1, the backward is one multiply."""
+
+    @staticmethod
+    @on_device_of(1)
+    def forward(ctx, z1, z2, labels, temperature, gamma, mode, correct_grad):
+        n, d = z1.shape
+        N = 2 * n
+        z = torch.cat([z1, z2], dim=0)                                      # contrast_loss3.py:26
+        lab2 = torch.cat([labels, labels])                                  # (Tensor.repeat: 24 us of host time)
+        ws = torch.empty(N * 8 + 8, dtype=torch.float32, device=z.device)
+        dz = torch.empty(N, d, dtype=torch.float32, device=z.device)
+        probs = (nat.ProblemF32 * 1)()
+        _fused_problem(probs[0], z, lab2, N, d, temperature, gamma, mode, correct_grad, ws, dz)
+        nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), 1, _stream(z))
+        ctx.dz, ctx.n = dz, n
+        ctx.set_materialize_grads(False)
+        row_stats = ws[N * 4:N * 8].view(4, N)
+        ctx.mark_non_differentiable(row_stats)
+        return ws[N * 8 + 4:N * 8 + 8], row_stats
+
+    @staticmethod
+    def backward(ctx, g_scalars, _g_stats):
+        if g_scalars is None:
+            return (None,) * 7
+        dz = ctx.dz * g_scalars[0]
+        return dz[:ctx.n], dz[ctx.n:], None, None, None, None, None
+
+
 class _DirectSupCon(torch.autograd.Function):
     """The same two entry points without the ``torch.library`` dispatch, for eager callers.
 
@@ -292,6 +360,13 @@ def supcon_fwd_eager(z1, z2, labels, tri, temperature, gamma, mode, correct_grad
     if torch.compiler.is_compiling():
         scalars, row_stats, _, _, _ = supcon_fwd(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
         return scalars, row_stats
+    if (not use_tc and labels is not None and mode != nat.MODE_EXCL and z1.dim() == 2 and z1.shape == z2.shape
+            and z1.dtype == torch.float32 and z2.dtype == torch.float32 and z1.shape[1] <= nat.MAX_D
+            and fused_fits([tuple(z1.shape)], z1.device)):
+        _require_cuda(z1, z2, labels)
+        if labels.dtype != torch.int32 or labels.shape != (z1.shape[0],):
+            raise TypeError("labels must be int32[n]")
+        return _FusedSupCon.apply(z1.contiguous(), z2.contiguous(), labels, temperature, gamma, mode, correct_grad)
     return _DirectSupCon.apply(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
 
 
@@ -428,8 +503,24 @@ class GraphRunner:
         self.labels = torch.arange(n, dtype=torch.int32, device=device)
         self.g = torch.ones(1, dtype=torch.float32, device=device)
         hp = (float(temperature), float(gamma), int(mode))
+        fused = not use_tc and int(mode) != nat.MODE_EXCL and fused_fits([(n, d)], device)
+
+        def body_fused():
+            N = 2 * n
+            z = torch.cat([self.z1, self.z2], dim=0)
+            lab2 = torch.cat([self.labels, self.labels])
+            ws = torch.empty(N * 8 + 8, dtype=torch.float32, device=device)
+            dz = torch.empty(N, d, dtype=torch.float32, device=device)
+            probs = (nat.ProblemF32 * 1)()
+            _fused_problem(probs[0], z, lab2, N, d, hp[0], hp[1], hp[2], correct_grad, ws, dz)
+            nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), 1,
+                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            self._keep = (z, lab2, ws)
+            return ws[N * 8 + 4:N * 8 + 8], ws[N * 4:N * 8].view(4, N), dz
 
         def body():
+            if fused:
+                return body_fused()
             scalars, row_stats, zpack, labels_full, sig = supcon_fwd._init_fn(
                 self.z1, self.z2, self.labels, None, hp[0], hp[1], hp[2], bool(correct_grad), bool(use_tc))
             dz = supcon_bwd._init_fn(self.g, zpack, labels_full, sig, None, row_stats, scalars, hp[0], hp[1], hp[2],
@@ -662,16 +753,22 @@ class _GroupSupCon(torch.autograd.Function):
             N = 2 * n
             z = torch.cat([views[2 * k], views[2 * k + 1]], dim=0)          # contrast_loss3.py:26
             zs.append(z)
-            base = ws[offs[k]:]
-            acc, stats = base[:N * 4], base[N * 4:N * 8]
-            partials, scalars = base[N * 8:N * 8 + 4], base[N * 8 + 4:N * 8 + 8]
-            scal.append(scalars)
-            q = probs[k]
+            scal.append(ws[offs[k] + N * 8 + 4:offs[k] + N * 8 + 8])
+            base = ws.data_ptr() + offs[k] * 4          # acc | row_stats | partials | scalars (pointer arithmetic:
+            q = probs[k]                                # every tensor slice costs ~3 us on the host)
             q.z, q.n_total, q.d, q.ldz, q.labels = z.data_ptr(), N, d, z.stride(0), labels[k].data_ptr()
             q.inv_tau, q.gamma, q.mode, q.correct_grad = 1.0 / float(temperature), float(gamma), int(mode), int(bool(cg))
-            q.acc, q.row_stats, q.stats_stride = acc.data_ptr(), stats.data_ptr(), N
-            q.partials, q.scalars = partials.data_ptr(), scalars.data_ptr()
-        nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(probs), K, st)
+            q.acc, q.row_stats, q.stats_stride = base, base + N * 16, N
+            q.partials, q.scalars = base + N * 32, base + N * 32 + 16
+        ctx.fused = fused_fits(shapes, dev)
+        if ctx.fused:
+            # forward AND backward (upstream gradient 1) in one cooperative launch; backward() only scales
+            ctx.dz = [torch.empty(2 * n, d, dtype=torch.float32, device=dev) for n, d in shapes]
+            for k, dz in enumerate(ctx.dz):
+                probs[k].dz, probs[k].lddz = dz.data_ptr(), dz.stride(0)
+            nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), K, st)
+        else:
+            nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(probs), K, st)
         ctx.probs, ctx.keep, ctx.shapes = probs, (ws, zs, labels), shapes
         return tuple(scal)
 
@@ -680,6 +777,15 @@ class _GroupSupCon(torch.autograd.Function):
         probs, shapes = ctx.probs, ctx.shapes
         K = len(shapes)
         ws, zs, labels = ctx.keep
+        if ctx.fused:
+            grads = []
+            for k, (n, d) in enumerate(shapes):
+                if g_scalars[k] is None:
+                    grads += [None, None]
+                else:
+                    dz = ctx.dz[k] * g_scalars[k][0]
+                    grads += [dz[:n], dz[n:]]
+            return (None, None, *grads)
         st = _stream(ws)
         grads, hold = [], []
         for k, (n, d) in enumerate(shapes):
@@ -745,8 +851,13 @@ class GroupGraphRunner:
         self.z_dst = [h for (n, _), z in zip(self.shapes, self.z) for h in (z[:n], z[n:])]
         self.lab_dst = [h for (n, _), l in zip(self.shapes, self.lab) for h in (l[:n], l[n:])]
 
+        self.fused = fused_fits(self.shapes, device)
+
         def body():
             st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            if self.fused:                       # the whole step's losses and their gradients: ONE kernel
+                nat.call("spcl_supcon_group_fused_f32", ctypes.byref(self.probs), self.K, st)
+                return
             nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(self.probs), self.K, st)
             nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(self.probs), self.K, st)
 

@@ -692,3 +692,62 @@ def test_wide_backward_kernel_against_the_oracle(n, run, mode, gamma):
     # the two backward kernels evaluate the same T (same epilogue code) and differ only in accumulation order
     g, b = np.concatenate([res["dz1"], res["dz2"]]), np.concatenate([base["dz1"], base["dz2"]])
     assert np.abs(g - b).max() <= 2e-3 * np.abs(b).max(), np.abs(g - b).max() / np.abs(b).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# the two fp32 routes of the reference's own batch sizes: one cooperative launch (default) / one launch per stage
+# ------------------------------------------------------------------------------------------------
+def test_fused_small_batch_route_is_taken_where_it_fits():
+    from spcl_b200 import ops
+    cap = ops.fused_capacity("cuda")
+    assert cap >= 148, cap                                       # at least one CTA per SM on a B200
+    assert ops.fused_fits([(256, 256)] * 3, "cuda")              # cfg2: 3 x 64 tiles
+    assert not ops.fused_fits([(2048, 128)], "cuda")             # 64 x 64 tiles: the multi-launch kernels take it
+    assert not ops.fused_fits([(64, 128)] * 3 + [(4096, 64)], "cuda")
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("name", ["sp_soft_g5_cg0_patient", "sp_hard_g2_cg1_partition", "supcon1_partition",
+                                  "sp_soft_g5_cg0_simclr_none", "sp_soft_g5_cg0_tensor_target",
+                                  "sp_soft_g5_cg0_partition_t0.2", "sp_hard_g5_cg0_composite"])
+def test_fp32_routes_match_reference_cfg1(name, fused, monkeypatch):
+    """Both routes against the goldens of the unmodified reference (the route is chosen per call from the
+    environment); the case names are a subset of CFG1.cases."""
+    assert name in CFG1.cases
+    monkeypatch.setenv("SPCL_FUSED_SMALL", fused)
+    kw = parse_cfg1_case(name, CFG1)
+    res = _run(CFG1["z1"], CFG1["z2"], precision="fp32", **kw)
+    ref = CFG1.case(name)
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL), (res["loss"], ref["loss"])
+    if kw["cls"] != "SupConLoss1":
+        assert np.isclose(res["ratio"], ref["ratio"], rtol=1e-5, atol=1e-7)
+    assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL
+
+
+@pytest.mark.parametrize("name", CFG2.cases)
+def test_multi_launch_fp32_route_matches_reference_cfg2(name, monkeypatch):
+    monkeypatch.setenv("SPCL_FUSED_SMALL", "0")
+    z1, z2 = CFG2[f"{name}/z1"], CFG2[f"{name}/z2"]
+    res = _run(z1, z2, target=CFG2[f"{name}/labels"].tolist(), gamma=float(CFG2[f"{name}/gamma"]), mode="soft",
+               precision="fp32")
+    ref = CFG2.case(name)
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL)
+    assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL
+
+
+@pytest.mark.parametrize("n,d,mode,gamma", [(5, 16, "soft", 3.0), (97, 200, "hard", 4.0), (300, 256, "none", 1e6),
+                                            (544, 96, "soft", 6.0)])
+def test_fused_small_batch_against_the_oracle(n, d, mode, gamma):
+    """Ragged sizes (N not a multiple of the 64-anchor tile, d not a multiple of 16 / above 128: two column passes of
+    the dZ stage), up to the largest single problem the cooperative grid holds (17 x 17 tiles)."""
+    from spcl_b200 import ops
+    assert ops.fused_fits([(n, d)], "cuda")
+    labels = acdc_meta_labels(n)["patient"] if n > 8 else torch.tensor([0, 1, 0, 1, 0])
+    z1, z2 = make_views(labels, d, sigma=0.7, seed=3)
+    cls = "SupConLoss1" if mode == "none" else "SP"
+    res = _run(z1, z2, cls=cls, target=labels.tolist(), gamma=gamma, mode=mode, correct_grad=True, precision="fp32")
+    ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=gamma, mode=mode, correct_grad=True)
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL), (res["loss"], ref["loss"])
+    if mode != "none":
+        assert np.isclose(res["ratio"], ref["ratio"], rtol=1e-5, atol=1e-7)
+    assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL

@@ -1,2 +1,8 @@
-timeout 120 tools/mma_bench.bin 2>&1 | tee gpurun_out/r02zb_mma_bench.txt
-SPCL_B200_LIB=$PWD/variants/trace.so timeout 300 python tools/gpu_trace.py 16384 128 0 both 2>&1 | sed -n "/bwd_kernel/,\$p" > gpurun_out/r02zb_trace_wide.log; sed -n 1,3p gpurun_out/r02zb_trace_wide.log; sed -n 20,30p gpurun_out/r02zb_trace_wide.log
+SPCL_FUSED_STAMP=1 SPCL_B200_LIB=$PWD/variants/stamp.so timeout 300 python - <<'PY' 2>&1 | grep "spcl fused" | tail -4
+import sys; sys.path.insert(0, "tools"); sys.path.insert(0, ".")
+import torch, gpu_small
+print(gpu_small.raw_group_times(256, 256))
+torch.cuda.synchronize()
+PY
+timeout 300 python tools/gpu_small_profile.py 2>&1 | grep -v "^$" | cut -c1-150 | sed -n 1,12p
+timeout 300 python tools/gpu_small.py 2>&1 | grep "cfg"

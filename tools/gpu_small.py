@@ -28,8 +28,29 @@ def bench(fn, iters=200):
     return s.elapsed_time(e) / iters * 1e3
 
 
+def raw_group_times(n, d):
+    """GPU time of the K = 3 losses + gradients of a step through the C ABI alone (no Python between the launches that
+    matter: 50 queued repetitions between two events): the one cooperative launch vs the 7 launches of the staged route."""
+    import ctypes
+    from spcl_b200 import _native as nat, ops
+    meta = [(0.07, g, nat.MODE_SOFT, True) for g in (5.0, 3.5, 2.0)]
+    runner = ops.GroupGraphRunner([(n, d)] * 3, meta, torch.device("cuda"))
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fused = lambda: nat.call("spcl_supcon_group_fused_f32", ctypes.byref(runner.probs), 3, st)
+
+    def staged():
+        nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(runner.probs), 3, st)
+        nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(runner.probs), 3, st)
+    out = {"staged_us": bench(staged, 50)}
+    if runner.fused:
+        out["fused_us"] = bench(fused, 50)
+        out["graph_replay_us"] = bench(runner.graph.replay, 50)
+    return out
+
+
 def main():
     for name, n, d in (("cfg1", 64, 128), ("cfg2", 256, 256)):
+        print(f"{name}: C ABI only, K=3: {raw_group_times(n, d)}", flush=True)
         meta = acdc_meta_labels(n)
         kinds = ("partition", "patient", "cycle")
         gammas = (5.0, 3.5, 2.0)
