@@ -860,12 +860,17 @@ __global__ void __launch_bounds__(NT, 2) fused_group_kernel(const __grid_constan
 #endif
   FSTAMP(0);
   cg::grid_group grid = cg::this_grid();
-  __shared__ Smem sm;
-  __shared__ float ts[BM][BN + 1];
+  // Operand tiles are kept TRANSPOSED ([k][row], row stride 68 floats = 16-byte aligned): a thread reads its four rows /
+  // four columns of one k with ONE 128-bit shared load each, i.e. 2 LDS + 16 FMA per k step (the row-major tiles of
+  // tile_dot: 8 LDS + 16 FMA -- the stage was issue-bound: 57k of the kernel's 142k cycles at cfg2).
+  constexpr int LDT = BM + 4;
+  __shared__ __align__(16) float sa[BK][LDT];           // stage 1: Z_I^T chunk | stage 4: first half of the Z_J block
+  __shared__ __align__(16) float sb[BK][LDT];           // stage 1: Z_J^T chunk | stage 4: second half
+  __shared__ __align__(16) float tt[BN][LDT];           // stage 4: T^T  [column j][row i]
   __shared__ float rstat[3][BM], cstat[3][BN];          // logD | 1/c | u of the tile's rows / columns
   __shared__ float red[3][2];
   const int k = blockIdx.z;
-  const Args& p = g.p[k];
+  const Args p = g.p[k];                                 // (a register copy: g.p[k] is a dynamically indexed constant load)
   const bool active = blockIdx.x < g.gx[k] && blockIdx.y < g.gy[k];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * BM, j0 = static_cast<int64_t>(blockIdx.y) * BN;
@@ -895,10 +900,49 @@ __global__ void __launch_bounds__(NT, 2) fused_group_kernel(const __grid_constan
     split_rows(p, i0, ty, gi, li);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      gj[b] = j0 + tx + 16 * b;
+      gj[b] = j0 + 4 * tx + b;                           // four CONSECUTIVE columns per thread (one float4 of sb)
       lj[b] = gj[b] < p.N ? p.labels[gj[b]] : 0;
     }
-    tile_dot(p, sm, i0, j0, d);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) d[a][b] = 0.f;
+    // the next chunk's 2 x 8 operand values per thread are fetched into registers while this chunk is multiplied: with
+    // load -> store -> barrier -> multiply in series every chunk paid a full L2 round trip (4.2k cycles per chunk
+    // against 1.2k of arithmetic at cfg1)
+    float pa[(BM * BK) / NT], pb[(BM * BK) / NT];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int t = 0; t < (BM * BK) / NT; ++t) {
+        const int idx = tid + t * NT;
+        const int r = idx / BK, kk = idx % BK;
+        const bool kok = (k0 + kk) < p.d;
+        pa[t] = (kok && i0 + r < p.N) ? p.z[(i0 + r) * p.ldz + k0 + kk] : 0.f;
+        pb[t] = (kok && j0 + r < p.N) ? p.z[(j0 + r) * p.ldz + k0 + kk] : 0.f;
+      }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.d; k0 += BK) {
+#pragma unroll
+      for (int t = 0; t < (BM * BK) / NT; ++t) {
+        const int idx = tid + t * NT;
+        sa[idx % BK][idx / BK] = pa[t];
+        sb[idx % BK][idx / BK] = pb[t];
+      }
+      __syncthreads();
+      if (k0 + BK < p.d) fetch(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 ra = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+        const float4 rb = *reinterpret_cast<const float4*>(&sb[kk][tx * 4]);
+        const float av[4] = {ra.x, ra.y, ra.z, ra.w}, bv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) d[a][b] = fmaf(av[a], bv[b], d[a][b]);
+      }
+      __syncthreads();
+    }
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -1022,54 +1066,81 @@ __global__ void __launch_bounds__(NT, 2) fused_group_kernel(const __grid_constan
   __syncthreads();
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    const int cj = tx + 16 * b;
+    const int cj = 4 * tx + b;
     const float ldj = cstat[0][cj], icj = cstat[1][cj], uj = cstat[2][cj];
+    float tv[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int ri = ty * 4 + a;
-      float tv = 0.f;
+      tv[a] = 0.f;
       if (gj[b] < p.N && gi[a] < p.N && gi[a] != gj[b]) {
         const float s = d[a][b] * p.inv_tau;
-        tv = expf(s - shift) * (rstat[2][ri] + uj);
+        tv[a] = expf(s - shift) * (rstat[2][ri] + uj);
         if (li[a] == lj[b])
-          tv -= sp_weight(rstat[0][ri] - s, p.gamma, p.inv_gamma, p.mode) * rstat[1][ri] +
-                sp_weight(ldj - s, p.gamma, p.inv_gamma, p.mode) * icj;
+          tv[a] -= sp_weight(rstat[0][ri] - s, p.gamma, p.inv_gamma, p.mode) * rstat[1][ri] +
+                   sp_weight(ldj - s, p.gamma, p.inv_gamma, p.mode) * icj;
       }
-      ts[ri][cj] = tv;
     }
+    *reinterpret_cast<float4*>(&tt[cj][ty * 4]) = make_float4(tv[0], tv[1], tv[2], tv[3]);     // T^T: rows of column cj
   }
-  __syncthreads();
   const float coef = scale / n_total * p.inv_tau;      // upstream gradient 1
-  const int jmax = static_cast<int>(min(static_cast<int64_t>(BN), p.N - j0));
-  for (int c0 = 0; c0 < p.d; c0 += 128) {              // 8 columns per thread and pass: dzacc stays in 32 registers
-    float dzacc[4][8];
+  // dZ_I [64 x d] += T [64 x 64] Z_J [64 x d], 64 columns of d at a time: the Z_J block is staged in sa | sb
+  // ([j][column], 32 rows each), K = the tile's 64 columns j; columns past N carry T = 0 and zero-filled Z rows.
+  // (the next block is fetched into registers under this block's arithmetic, as in stage 1; the four columns of a
+  // thread are contiguous, so the accumulation into dz is one 16-byte red.global.add.v4.f32 per row where dz allows it:
+  // the scalar atomics, 16-byte strided across the lanes, were most of this stage's time)
+  float pz[(BN * 64) / NT];
+  auto fetch_z = [&](int c0) {
+#pragma unroll
+    for (int t = 0; t < (BN * 64) / NT; ++t) {
+      const int idx = tid + t * NT;
+      const int jj = idx >> 6, col = idx & 63;
+      pz[t] = (j0 + jj < p.N && c0 + col < p.d) ? p.z[(j0 + jj) * p.ldz + c0 + col] : 0.f;
+    }
+  };
+  const bool vec_ok = (lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0;
+  fetch_z(0);
+  for (int c0 = 0; c0 < p.d; c0 += 64) {
+    __syncthreads();                                   // tt written / the previous block's sa, sb reads are done
+#pragma unroll
+    for (int t = 0; t < (BN * 64) / NT; ++t) {
+      const int idx = tid + t * NT;
+      const int jj = idx >> 6, col = idx & 63;
+      if (jj < BK) sa[jj][col] = pz[t];
+      else sb[jj - BK][col] = pz[t];
+    }
+    __syncthreads();
+    if (c0 + 64 < p.d) fetch_z(c0 + 64);
+    float acc4[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dzacc[a][c] = 0.f;
-#pragma unroll 4
-    for (int jj = 0; jj < jmax; ++jj) {
-      const float* zrow = p.z + (j0 + jj) * p.ldz + c0;
-      float tv[4];
+      for (int c = 0; c < 4; ++c) acc4[a][c] = 0.f;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) tv[a] = ts[ty * 4 + a][jj];
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll 8
+      for (int jj = 0; jj < BK; ++jj) {
+        const float4 rt = *reinterpret_cast<const float4*>(&tt[h * BK + jj][ty * 4]);
+        const float4 rz = *reinterpret_cast<const float4*>(h ? &sb[jj][tx * 4] : &sa[jj][tx * 4]);
+        const float tv4[4] = {rt.x, rt.y, rt.z, rt.w}, zv4[4] = {rz.x, rz.y, rz.z, rz.w};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int col = tx + 16 * c;
-        const float zv = (c0 + col) < p.d ? zrow[col] : 0.f;
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) dzacc[a][c] = fmaf(tv[a], zv, dzacc[a][c]);
+          for (int c = 0; c < 4; ++c) acc4[a][c] = fmaf(tv4[a], zv4[c], acc4[a][c]);
       }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       if (gi[a] >= p.N) continue;
-      float* out = dz + gi[a] * lddz + c0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int col = tx + 16 * c;
-        if (c0 + col < p.d) atomicAdd(out + col, dzacc[a][c] * coef);
+      float* out = dz + gi[a] * lddz + c0 + 4 * tx;
+      if (vec_ok && c0 + 4 * tx + 3 < p.d) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(acc4[a][0] * coef),
+                     "f"(acc4[a][1] * coef), "f"(acc4[a][2] * coef), "f"(acc4[a][3] * coef) : "memory");
+        continue;
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c0 + 4 * tx + c < p.d) atomicAdd(out + c, acc4[a][c] * coef);
     }
   }
 #if SPCL_FUSED_STAMP

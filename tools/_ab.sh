@@ -1,8 +1,7 @@
-SPCL_FUSED_STAMP=1 SPCL_B200_LIB=$PWD/variants/stamp.so timeout 300 python - <<'PY' 2>&1 | grep "spcl fused" | tail -4
+cat > /tmp/raw.py <<'PY'
 import sys; sys.path.insert(0, "tools"); sys.path.insert(0, ".")
 import torch, gpu_small
 print(gpu_small.raw_group_times(256, 256))
-torch.cuda.synchronize()
 PY
-timeout 300 python tools/gpu_small_profile.py 2>&1 | grep -v "^$" | cut -c1-150 | sed -n 1,12p
-timeout 300 python tools/gpu_small.py 2>&1 | grep "cfg"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_group -s 20 -c 1 -f -o gpurun_out/r02zd_prof_fused python /tmp/raw.py > gpurun_out/r02zd_ncu_fused.log 2>&1
+ls -la gpurun_out/r02zd_prof_fused.ncu-rep
