@@ -2294,7 +2294,7 @@ static bool pair_enabled() {
     const char* e = std::getenv("SPCL_PAIR");
     env = (e == nullptr) ? SPCL_PAIR_DEFAULT : (e[0] != '0');
   }
-  return env != 0 && !(g_dbg & 32);
+  return (env != 0 || (g_dbg & 32768)) && !(g_dbg & 32);      // debug flag 32768 selects it at run time (tests)
 }
 
 // SPCL_SYM=0 switches the symmetric stats pass off (development A/B switch); so does debug flag 64

@@ -665,13 +665,15 @@ def test_all_positive_tiles_against_the_oracle(mode, gamma, cg):
         assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (run, rel, cos)
 
 
+@pytest.mark.parametrize("flag", [16384, 32768], ids=["wide", "cta_pair"])
 @pytest.mark.parametrize("n,run,mode,gamma", [(1024, 256, "soft", 6.0), (1024, 96, "hard", 5.5), (1536, 1, "none", 1e6),
                                               (4096, 1, "soft", 8.0)])
-def test_wide_backward_kernel_against_the_oracle(n, run, mode, gamma):
-    """`bwd_wide_kernel` (128 x 256 S tiles, opt-in: SPCL_BWD_WIDE=1 / debug flag 16384; see
-    profiles/r02zb_bwd_wide_experiment.txt) against the fp64 oracle, same tolerances as the default backward:
-    all-positive, mixed and SimCLR labellings; 2 n / 128 column tiles = 16 ... 64 (pairs that wrap the slot ring
-    included: the ring holds five tiles)."""
+def test_optional_backward_kernels_against_the_oracle(n, run, mode, gamma, flag):
+    """The two opt-in backward kernels against the fp64 oracle, same tolerances as the default backward:
+    `bwd_wide_kernel` (128 x 256 S tiles: SPCL_BWD_WIDE=1 / debug flag 16384; profiles/r02zb_bwd_wide_experiment.txt) and
+    `bwd2_kernel` (a CTA pair per 256 anchor rows, `tcgen05 cta_group::2`: SPCL_PAIR=1 / debug flag 32768).
+    All-positive, mixed and SimCLR labellings; 2 n / 128 column tiles = 16 ... 64 (pairs that wrap the wide kernel's
+    five-tile slot ring included)."""
     import ctypes
     h = nat.lib()
     h.spcl_debug_set_flags.argtypes = [ctypes.c_int]
@@ -680,7 +682,7 @@ def test_wide_backward_kernel_against_the_oracle(n, run, mode, gamma):
     z1, z2 = make_views(labels, d, sigma=0.7, seed=11)
     z1, z2 = z1.bfloat16().float(), z2.bfloat16().float()
     cls = "SupConLoss1" if mode == "none" else "SP"
-    h.spcl_debug_set_flags(16384)
+    h.spcl_debug_set_flags(flag)
     try:
         res = _run(z1, z2, cls=cls, target=labels.int().numpy(), gamma=gamma, mode=mode, precision="bf16", validate=False)
     finally:
@@ -689,9 +691,11 @@ def test_wide_backward_kernel_against_the_oracle(n, run, mode, gamma):
     ref = supcon_closed_form(z1.numpy(), z2.numpy(), target=labels.tolist(), gamma=gamma, mode=mode)
     rel, cos = _grad_metrics(res, ref)
     assert rel < BF16_TIGHT_GRAD_REL and cos > BF16_TIGHT_COS, (rel, cos)
-    # the two backward kernels evaluate the same T (same epilogue code) and differ only in accumulation order
-    g, b = np.concatenate([res["dz1"], res["dz2"]]), np.concatenate([base["dz1"], base["dz2"]])
-    assert np.abs(g - b).max() <= 2e-3 * np.abs(b).max(), np.abs(g - b).max() / np.abs(b).max()
+    # the backward kernels evaluate the same T and differ in the accumulation order of S and dZ only; under the hard
+    # rule a pair within rounding of gamma may take the other weight in the other kernel, so only the oracle bound applies
+    if mode != "hard":
+        g, b = np.concatenate([res["dz1"], res["dz2"]]), np.concatenate([base["dz1"], base["dz2"]])
+        assert np.abs(g - b).max() <= 2e-3 * np.abs(b).max(), np.abs(g - b).max() / np.abs(b).max()
 
 
 # ------------------------------------------------------------------------------------------------
