@@ -16,6 +16,7 @@ LIB_PATH = pathlib.Path(os.environ.get("SPCL_B200_LIB", _PKG_DIR / "libspcl_b200
 BUILD_SCRIPT = _PKG_DIR / "csrc" / "build.sh"
 
 MODE_NONE, MODE_HARD, MODE_SOFT, MODE_EXCL = 0, 1, 2, 3
+ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DRIVER = -1, -2, -3, -4
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 TILE = 128
 MAX_D = 256

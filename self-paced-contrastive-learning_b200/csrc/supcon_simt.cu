@@ -1431,8 +1431,15 @@ extern "C" int spcl_supcon_group_fused_f32(const spcl_problem_f32* problems, int
   if (ctas > simt::fused_capacity()) return SPCL_ERR_UNSUPPORTED;     // the grid-wide barrier needs every CTA resident
   int sp = (any_sp ? 1 : 0) | (std::getenv("SPCL_FUSED_STAMP") != nullptr ? 2 : 0);   // debug: phase times of CTA 0
   void* args[] = {&g, &sp};
-  SPCL_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(simt::fused_group_kernel),
-                                            dim3(gx, gy, static_cast<unsigned>(count)), dim3(simt::NT), args, 0,
-                                            static_cast<cudaStream_t>(stream)));
+  const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(simt::fused_group_kernel),
+                                                    dim3(gx, gy, static_cast<unsigned>(count)), dim3(simt::NT), args, 0,
+                                                    static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+    // fewer SMs than the occupancy query assumed (MPS / partitioned contexts): nothing was launched, the caller falls
+    // back to the staged entry points
+    (void)cudaGetLastError();
+    return SPCL_ERR_UNSUPPORTED;
+  }
+  SPCL_CUDA_TRY(e);
   return SPCL_OK;
 }

@@ -287,6 +287,19 @@ def fused_fits(shapes, device) -> bool:
     return tiles * tiles * len(shapes) <= fused_capacity(device)
 
 
+def _fused_launch(probs, count: int, st, device) -> bool:
+    """``spcl_supcon_group_fused_f32``; False when the library declines (the cooperative grid cannot be resident on
+    this context after all, e.g. an SM-partitioned one): the route is then switched off for the device and the caller
+    runs the staged entry points.  Any other error raises."""
+    rc = nat.lib().spcl_supcon_group_fused_f32(ctypes.byref(probs), count, st)
+    if rc == nat.ERR_UNSUPPORTED:
+        idx = torch.device(device).index
+        _FUSED_CAP[torch.cuda.current_device() if idx is None else idx] = 0
+        return False
+    nat.check(rc, "spcl_supcon_group_fused_f32")
+    return True
+
+
 def _fused_problem(q, z, labels2, N, d, temperature, gamma, mode, correct_grad, ws, dz):
     """Fill one ``spcl_problem_f32`` from the workspace ``ws`` = acc [N,4] | row_stats [4,N] | partials [4] | scalars [4]."""
     q.z, q.n_total, q.d, q.ldz, q.labels = z.data_ptr(), N, d, z.stride(0), labels2.data_ptr()
@@ -295,6 +308,10 @@ def _fused_problem(q, z, labels2, N, d, temperature, gamma, mode, correct_grad, 
     q.acc, q.row_stats, q.stats_stride = base, base + N * 16, N
     q.partials, q.scalars = base + N * 32, base + N * 32 + 16
     q.dz, q.lddz = dz.data_ptr(), dz.stride(0)
+
+
+class _FusedDeclined(Exception):
+    pass
 
 
 class _FusedSupCon(torch.autograd.Function):
@@ -312,7 +329,8 @@ class _FusedSupCon(torch.autograd.Function):
         dz = torch.empty(N, d, dtype=torch.float32, device=z.device)
         probs = (nat.ProblemF32 * 1)()
         _fused_problem(probs[0], z, lab2, N, d, temperature, gamma, mode, correct_grad, ws, dz)
-        nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), 1, _stream(z))
+        if not _fused_launch(probs, 1, _stream(z), z.device):
+            raise _FusedDeclined()
         ctx.dz, ctx.n = dz, n
         ctx.set_materialize_grads(False)
         row_stats = ws[N * 4:N * 8].view(4, N)
@@ -366,7 +384,10 @@ def supcon_fwd_eager(z1, z2, labels, tri, temperature, gamma, mode, correct_grad
         _require_cuda(z1, z2, labels)
         if labels.dtype != torch.int32 or labels.shape != (z1.shape[0],):
             raise TypeError("labels must be int32[n]")
-        return _FusedSupCon.apply(z1.contiguous(), z2.contiguous(), labels, temperature, gamma, mode, correct_grad)
+        try:
+            return _FusedSupCon.apply(z1.contiguous(), z2.contiguous(), labels, temperature, gamma, mode, correct_grad)
+        except _FusedDeclined:
+            pass                                     # (fused_fits is False for this device from now on)
     return _DirectSupCon.apply(z1, z2, labels, tri, temperature, gamma, mode, correct_grad, use_tc)
 
 
@@ -513,8 +534,9 @@ class GraphRunner:
             dz = torch.empty(N, d, dtype=torch.float32, device=device)
             probs = (nat.ProblemF32 * 1)()
             _fused_problem(probs[0], z, lab2, N, d, hp[0], hp[1], hp[2], correct_grad, ws, dz)
-            nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), 1,
-                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            if not _fused_launch(probs, 1, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream), device):
+                raise nat.SpclError("the cooperative small-batch launch was declined on this context: set "
+                                    "SPCL_FUSED_SMALL=0 to capture the staged route")
             self._keep = (z, lab2, ws)
             return ws[N * 8 + 4:N * 8 + 8], ws[N * 4:N * 8].view(4, N), dz
 
@@ -766,8 +788,10 @@ class _GroupSupCon(torch.autograd.Function):
             ctx.dz = [torch.empty(2 * n, d, dtype=torch.float32, device=dev) for n, d in shapes]
             for k, dz in enumerate(ctx.dz):
                 probs[k].dz, probs[k].lddz = dz.data_ptr(), dz.stride(0)
-            nat.call("spcl_supcon_group_fused_f32", ctypes.byref(probs), K, st)
-        else:
+            ctx.fused = _fused_launch(probs, K, st, dev)
+            if not ctx.fused:
+                ctx.dz = None
+        if not ctx.fused:
             nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(probs), K, st)
         ctx.probs, ctx.keep, ctx.shapes = probs, (ws, zs, labels), shapes
         return tuple(scal)
@@ -856,8 +880,9 @@ class GroupGraphRunner:
         def body():
             st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             if self.fused:                       # the whole step's losses and their gradients: ONE kernel
-                nat.call("spcl_supcon_group_fused_f32", ctypes.byref(self.probs), self.K, st)
-                return
+                self.fused = _fused_launch(self.probs, self.K, st, device)
+                if self.fused:
+                    return
             nat.call("spcl_supcon_group_fwd_f32", ctypes.byref(self.probs), self.K, st)
             nat.call("spcl_supcon_group_bwd_f32", ctypes.byref(self.probs), self.K, st)
 

@@ -755,3 +755,32 @@ def test_fused_small_batch_against_the_oracle(n, d, mode, gamma):
     if mode != "none":
         assert np.isclose(res["ratio"], ref["ratio"], rtol=1e-5, atol=1e-7)
     assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL
+
+
+def test_declined_cooperative_launch_falls_back_to_the_staged_route(monkeypatch):
+    """`spcl_supcon_group_fused_f32` may decline (SPCL_ERR_UNSUPPORTED: the cooperative grid cannot be resident, e.g. on an
+    SM-partitioned context); single calls and grouped calls must then produce the same results on the staged kernels."""
+    from spcl_b200 import ops
+    declined = []
+
+    def decline(probs, count, st, device):
+        declined.append(count)
+        return False
+    monkeypatch.setattr(ops, "_fused_launch", decline)
+    name = CFG2.cases[0]
+    z1, z2 = CFG2[f"{name}/z1"], CFG2[f"{name}/z2"]
+    labels, gamma = CFG2[f"{name}/labels"].tolist(), float(CFG2[f"{name}/gamma"])
+    res = _run(z1, z2, target=labels, gamma=gamma, mode="soft", precision="fp32")
+    ref = CFG2.case(name)
+    assert declined == [1]
+    assert np.isclose(res["loss"], ref["loss"], rtol=FP32_LOSS_RTOL)
+    assert _grad_metrics(res, ref)[0] < FP32_GRAD_REL
+    crit = spcl_b200.SelfPacedSupConLoss(weight_update="soft", precision="fp32")
+    crit.set_gamma(gamma)
+    a, b = torch.as_tensor(z1).cuda().requires_grad_(True), torch.as_tensor(z2).cuda().requires_grad_(True)
+    (loss,) = spcl_b200.grouped_forward([crit], [(a, b)], [labels])
+    loss.backward()
+    assert declined == [1, 1]
+    assert np.isclose(loss.item(), ref["loss"], rtol=FP32_LOSS_RTOL)
+    got = dict(dz1=a.grad.cpu().numpy(), dz2=b.grad.cpu().numpy())
+    assert _grad_metrics(got, ref)[0] < FP32_GRAD_REL

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "optional_backward" 2>&1 | tail -15
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r02zh_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/r02zh_smoke.log
