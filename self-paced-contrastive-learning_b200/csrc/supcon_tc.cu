@@ -536,24 +536,47 @@ __device__ __forceinline__ void stats_chunk_slow_sym(const uint32_t (&v)[32], in
   if (ce != 0.f) atomicAdd(reinterpret_cast<float*>(acc_cols + ch * 32 + lane), ce);
 }
 
+// 128-bit loads from the shared window (labels / column statistics staged with the slot): the generic-pointer loads the
+// compiler emits for `lab_s[cidx]` sat, one per element, inside the short-circuit branch of the positive test.
+__device__ __forceinline__ void lds_v4i(uint32_t addr, int& a, int& b, int& c, int& d) {
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+
+template <int MODE>
+__device__ __forceinline__ float sp_w(float l, float gamma, float inv_gamma) {
+  if (MODE == SPCL_MODE_HARD) return l <= gamma ? 1.f : 0.f;
+  if (MODE == SPCL_MODE_SOFT) return fmaxf(1.f - l * inv_gamma, 0.f);
+  return 1.f;
+}
+
 // sp pass: positives of this row in 32 columns.  cnt += P;  NONE: wl += P <z_i, z_j>;  hard / soft: wl += P W LLH,
-// wp += P W with W from the final logD_i.
+// wp += P W with W from the final logD_i.  Branch free: every element is predicate arithmetic + selects, the labels come
+// in with one LDS.128 per four columns.  (r02zi timeline: the branchy form -- a dependent generic load per element
+// behind `(cidx < jmax) && (cidx != jdiag) && (lab_s[cidx] == li)`, the weighting rule a run-time switch -- took 22 700
+// cycles per tile, 177 per element: sp_kernel 29 us at cfg3 for four tiles per CTA.)
+template <int MODE>
 __device__ __forceinline__ void sp_chunk(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
                                          const int32_t* lab_s, const Params& p, float logD, float& wl, float& wp,
                                          float& cnt) {
+  const uint32_t la = smem_u32(lab_s + ch * 32);
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const int cidx = ch * 32 + e;
-    const float dot = __uint_as_float(v[e]);
-    const bool pos = (cidx < jmax) && (cidx != jdiag) && (lab_s[cidx] == li);
-    cnt += pos ? 1.f : 0.f;
-    if (p.mode == SPCL_MODE_NONE) {
-      wl += pos ? dot : 0.f;
-    } else {
-      const float l = fmaf(-dot, p.inv_tau, logD);          // l_ij = logD_i - S_ij
-      const float w = pos ? sp_weight(l, p.gamma, p.inv_gamma, p.mode) : 0.f;
-      wl = fmaf(w, -l, wl);
-      wp += w;
+  for (int e0 = 0; e0 < 32; e0 += 4) {
+    int lab[4];
+    lds_v4i(la + e0 * 4, lab[0], lab[1], lab[2], lab[3]);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int cidx = ch * 32 + e0 + h;
+      const float dot = __uint_as_float(v[e0 + h]);
+      const bool pos = (cidx < jmax) & (cidx != jdiag) & (lab[h] == li);
+      cnt += pos ? 1.f : 0.f;
+      if (MODE == SPCL_MODE_NONE) {
+        wl += pos ? dot : 0.f;
+      } else {
+        const float l = fmaf(-dot, p.inv_tau, logD);        // l_ij = logD_i - S_ij
+        const float w = pos ? sp_w<MODE>(l, p.gamma, p.inv_gamma) : 0.f;
+        wl = fmaf(w, -l, wl);
+        wp += w;
+      }
     }
   }
 }
@@ -755,37 +778,39 @@ __device__ __forceinline__ void bwd_chunk_fast_swp(const uint32_t (&v)[32], uint
   stage_c(15);
 }
 
-template <int MODE>
-__device__ __forceinline__ float sp_w(float l, float gamma, float inv_gamma) {
-  if (MODE == SPCL_MODE_HARD) return l <= gamma ? 1.f : 0.f;
-  if (MODE == SPCL_MODE_SOFT) return fmaxf(1.f - l * inv_gamma, 0.f);
-  return 1.f;
-}
-
-// slow (branch free): T = valid E (u_i + u_j) - pos (W_ij / c_i + W_ji / c_j)
+// slow (branch free): T = valid E (u_i + u_j) - pos (W_ij / c_i + W_ji / c_j).  Labels and column statistics of four
+// columns at a time with 128-bit loads from the shared window (see sp_chunk).
 template <int MODE>
 __device__ __forceinline__ void bwd_chunk_slow(const uint32_t (&v)[32], int ch, int jdiag, int jmax, int li,
                                                const int32_t* lab_s, const float* logD_s, const float* invc_s,
                                                const float* u_s, const Params& p, float logD_i, float invc_i,
                                                float u_i, uint32_t (&pk)[16]) {
+  const uint32_t la = smem_u32(lab_s + ch * 32), lda = smem_u32(logD_s + ch * 32), ica = smem_u32(invc_s + ch * 32),
+                 ua = smem_u32(u_s + ch * 32);
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    float tv[2];
+  for (int e = 0; e < 32; e += 4) {
+    int lab[4];
+    float ldj[4], icj[4], uj[4], tv[4];
+    lds_v4i(la + e * 4, lab[0], lab[1], lab[2], lab[3]);
+    lds_v4(lda + e * 4, ldj[0], ldj[1], ldj[2], ldj[3]);
+    lds_v4(ica + e * 4, icj[0], icj[1], icj[2], icj[3]);
+    lds_v4(ua + e * 4, uj[0], uj[1], uj[2], uj[3]);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
       const int cidx = ch * 32 + e + h;
       const float dot = __uint_as_float(v[e + h]);
-      const bool valid = (cidx < jmax) && (cidx != jdiag);
-      const bool pos = valid && (lab_s[cidx] == li);
+      const bool valid = (cidx < jmax) & (cidx != jdiag);
+      const bool pos = valid & (lab[h] == li);
       const float ex = ex2_approx(fmaf(dot, p.c2, -p.c2));
       const float s = dot * p.inv_tau;
       const float w = sp_w<MODE>(logD_i - s, p.gamma, p.inv_gamma) * invc_i +
-                      sp_w<MODE>(logD_s[cidx] - s, p.gamma, p.inv_gamma) * invc_s[cidx];
-      float t = valid ? ex * (u_i + u_s[cidx]) : 0.f;
+                      sp_w<MODE>(ldj[h] - s, p.gamma, p.inv_gamma) * icj[h];
+      float t = valid ? ex * (u_i + uj[h]) : 0.f;
       t -= pos ? w : 0.f;
       tv[h] = t;
     }
     pk[e >> 1] = pack_bf16x2(tv[0], tv[1]);
+    pk[(e >> 1) + 1] = pack_bf16x2(tv[2], tv[3]);
   }
 }
 
@@ -1032,6 +1057,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
   Barriers* bar = sm.bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  TRACE(0, 62u, 0);                                      // (timeline builds: kernel entry / prologue done / exit)
   if (warp == kMmaWarp0 && lane == 0) init_barriers(bar, /*slot: MMA commit + 4 epilogue warps*/ 5, 4, /*a_empty*/ 2);
   if (warp == kAllocWarp) tmem_alloc<kTmemCols>(&bar->tmem_base);
   if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tmap);
@@ -1048,6 +1074,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = bar->tmem_base;
   const uint32_t tmem_u = __shfl_sync(kFullMask, tmem_base, 0);
+  TRACE(0, 62u, 1);
 
   int64_t f0, f1;
   cta_range(p, f0, f1);
@@ -1072,6 +1099,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const int slot = it % p.nslot;
           const uint32_t ph = (it / p.nslot) & 1;
           mbar_wait(&bar->empty[slot], ph ^ 1);
+          TRACE(0, it, 0);
           mbar_arrive_expect_tx(&bar->full[slot], tile_tx);
           uint8_t* dst = sm.slot(slot);
           for (int c = 0; c < p.dc; ++c)
@@ -1101,6 +1129,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const uint32_t ph = (it / p.nslot) & 1, bph = (it / p.nbuf) & 1;
           mbar_wait_warp(&bar->full[slot], ph, lane);
           mbar_wait_warp(&bar->s_empty[buf], bph ^ 1, lane);
+          TRACE(1, it, 0);
           tc_fence_after();
           if (elect_one()) {
             issue_s_mma<TILE>(tmem_u + buf * TILE, a_base, smem_u32(sm.slot(slot)), 0, nk);
@@ -1108,6 +1137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
             tc_commit(&bar->s_full[buf]);
           }
           __syncwarp();
+          TRACE(1, it, 1);
         }
         ++it;
       });
@@ -1143,6 +1173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const int jmax = static_cast<int>(min(static_cast<int64_t>(TILE), p.N - j0));
           mbar_wait_warp(&bar->full[slot], ph, lane);
           mbar_wait_warp(&bar->s_full[buf], bph, lane);
+          TRACE(2 + warp, it, 0);
           tc_fence_after();
           const int32_t* lab_s = sm.slot_labels(slot);
           const uint32_t taddr = lane_base + buf * TILE;
@@ -1150,27 +1181,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
           const int4 csig = sigt[t];
           const bool allpos = rsig.x == rsig.y && csig.x == csig.y && csig.x == rsig.x && t * TILE != gi0 &&
                               jmax == TILE && !(p.dbg & 8192);
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32b_x32(taddr, va);
-          tmem_wait_ld();
+          // the chunk body (path x weighting rule) is chosen once per tile, outside the chunk loop
+          auto run_tile = [&](auto&& chunk_body) {
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr, va);
+            tmem_wait_ld();
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t(&cur)[32] = (ch & 1) ? vb : va;
-            uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
-            if (!allpos) sp_chunk(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
-            else if (p.mode == SPCL_MODE_SOFT) sp_chunk_allpos<SPCL_MODE_SOFT>(cur, p, logD, s0, s1);
-            else if (p.mode == SPCL_MODE_HARD) sp_chunk_allpos<SPCL_MODE_HARD>(cur, p, logD, s0, s1);
-            else sp_chunk_allpos<SPCL_MODE_NONE>(cur, p, logD, s0, s1);
-            if (ch < 3) tmem_wait_ld();
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+              uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+              if (ch < 3) tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, nxt);
+              chunk_body(cur, ch);
+              if (ch < 3) tmem_wait_ld();
+            }
+          };
+          if (!allpos) {
+            if (p.mode == SPCL_MODE_SOFT)
+              run_tile([&](const uint32_t(&cur)[32], int ch) {
+                sp_chunk<SPCL_MODE_SOFT>(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
+              });
+            else if (p.mode == SPCL_MODE_HARD)
+              run_tile([&](const uint32_t(&cur)[32], int ch) {
+                sp_chunk<SPCL_MODE_HARD>(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
+              });
+            else
+              run_tile([&](const uint32_t(&cur)[32], int ch) {
+                sp_chunk<SPCL_MODE_NONE>(cur, ch, jdiag, jmax, li, lab_s, p, logD, s0, s1, cnt);
+              });
+          } else {
+            if (p.mode == SPCL_MODE_SOFT)
+              run_tile([&](const uint32_t(&cur)[32], int) { sp_chunk_allpos<SPCL_MODE_SOFT>(cur, p, logD, s0, s1); });
+            else if (p.mode == SPCL_MODE_HARD)
+              run_tile([&](const uint32_t(&cur)[32], int) { sp_chunk_allpos<SPCL_MODE_HARD>(cur, p, logD, s0, s1); });
+            else
+              run_tile([&](const uint32_t(&cur)[32], int) { sp_chunk_allpos<SPCL_MODE_NONE>(cur, p, logD, s0, s1); });
+            cnt += static_cast<float>(TILE);
           }
-          if (allpos) cnt += static_cast<float>(TILE);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&bar->s_empty[buf]);
             mbar_arrive(&bar->empty[slot]);
           }
+          TRACE(2 + warp, it, 1);
         }
         ++it;
       });
@@ -1186,6 +1239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sp_kernel(const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  TRACE(0, 62u, 2);
   if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
