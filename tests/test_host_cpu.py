@@ -286,6 +286,32 @@ def test_group_abi_validates_arguments_without_touching_the_gpu():
         spcl_b200.grouped_forward([spcl_b200.SupConLoss1()], [], None)
 
 
+def test_fused_small_batch_abi_without_a_gpu(monkeypatch):
+    """The one-launch entry point validates like the staged ones, reports no capacity where no device answers, and the
+    host-side route selection follows the capacity and the SPCL_FUSED_SMALL switch."""
+    import re
+    h = nat.lib()
+    assert h.spcl_supcon_group_fused_f32(None, 3, None) == nat.ERR_INVALID_ARG
+    assert h.spcl_supcon_group_fused_f32(ctypes.byref((nat.ProblemF32 * 9)()), 9, None) == nat.ERR_UNSUPPORTED
+    assert h.spcl_supcon_group_fused_f32(ctypes.byref((nat.ProblemF32 * 2)()), 2, None) == nat.ERR_INVALID_ARG
+    if not torch.cuda.is_available():
+        assert h.spcl_supcon_fused_capacity() == 0
+    header = (ROOT / "include" / "spcl.h").read_text()
+    codes = dict(re.findall(r"#define (SPCL_ERR_\w+) \((-\d+)\)", header))
+    assert {k: int(v) for k, v in codes.items()} == {
+        "SPCL_ERR_INVALID_ARG": nat.ERR_INVALID_ARG, "SPCL_ERR_UNSUPPORTED": nat.ERR_UNSUPPORTED,
+        "SPCL_ERR_CUDA": nat.ERR_CUDA, "SPCL_ERR_NO_DRIVER": nat.ERR_NO_DRIVER}
+    from spcl_b200 import ops
+    monkeypatch.setattr(ops, "fused_capacity", lambda device: 296)
+    assert ops.fused_fits([(256, 256)] * 3, "cuda")                  # cfg2: 3 x 8 x 8 tiles
+    assert ops.fused_fits([(544, 96)], "cuda")                       # 17 x 17 tiles
+    assert not ops.fused_fits([(545, 96)], "cuda")                   # 18 x 18
+    assert not ops.fused_fits([(256, 256)] * 5, "cuda")              # 320 CTAs
+    assert not ops.fused_fits([], "cuda")
+    monkeypatch.setenv("SPCL_FUSED_SMALL", "0")
+    assert not ops.fused_fits([(64, 128)], "cuda")
+
+
 def test_dense_tail_rejects_what_is_not_on_the_hot_path():
     import spcl_b200
     with pytest.raises(NotImplementedError):
